@@ -1,0 +1,106 @@
+"""ctypes binding of libmwx_b200.so (the C ABI declared in include/mwx_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a call returns a non-zero status,
+this module raises.  ``python __graft_entry__.py build`` (or ``make -C fem_forth_perturb_b200/csrc``)
+produces the library in-tree.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmwx_b200.so')
+
+_lib = None
+
+i32, i64, f64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+_pi64 = ctypes.POINTER(ctypes.c_int64)
+_pi32 = ctypes.POINTER(ctypes.c_int32)
+_pf64 = ctypes.POINTER(ctypes.c_double)
+
+# name -> argtypes (device pointers and host arrays are passed as void*; host scalars by pointer)
+_SIGNATURES = {
+    'mwx_version': [],
+    'mwx_mesh_sort_columns': [i64, vp, vp],
+    'mwx_incidence': [i64, i64, i32, vp, vp, vp, vp],
+    'mwx_mesh_facets_count': [i64, i64, vp, vp, vp, vp, _pi64, vp],
+    'mwx_mesh_facets_fill': [i64, i64, vp, vp, vp, vp, i64, vp, vp, vp],
+    'mwx_mesh_refine': [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_element_dofs': [i64, i64, vp, vp, vp, vp],
+    'mwx_facet_element_count': [i64, i64, vp, vp, vp],
+    'mwx_pattern_count': [i64, i64, vp, vp, vp, vp, _pi64, _pi32, vp],
+    'mwx_pattern_fill': [i64, i64, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_assemble_morley': [i64, i64, vp, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp],
+    'mwx_assemble_penalty': [i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp, vp],
+    'mwx_axpby': [i64, f64, vp, f64, vp, vp, vp],
+    'mwx_condense_count': [i64, vp, vp, vp, vp, vp, _pi64, _pi64, vp],
+    'mwx_condense_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_spmv': [i64, vp, vp, vp, vp, vp, vp],
+    'mwx_csr_diagonal': [i64, vp, vp, vp, vp, vp],
+    'mwx_pcg_jacobi': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp],
+    'mwx_amg_setup_host': [i64, vp, vp, vp, f64, i32, i32, ctypes.POINTER(vp)],
+    'mwx_amg_num_levels': [vp],
+    'mwx_amg_level_dims': [vp, i32, i32, vp],
+    'mwx_amg_level_copy': [vp, i32, i32, vp, vp, vp],
+    'mwx_amg_level_splitting': [vp, i32, vp],
+    'mwx_amg_destroy_host': [vp],
+    'mwx_gs_wavefronts_host': [i64, vp, vp, vp, vp, _pi64],
+    'mwx_gs_wavefronts_backward_host': [i64, vp, vp, vp, vp, _pi64],
+    'mwx_amg_upload': [vp, i32, i32, vp, ctypes.POINTER(vp), vp],
+    'mwx_amg_level_rho': [vp, i32, _pf64],
+    'mwx_amg_destroy_dev': [vp],
+    'mwx_amg_vcycle': [vp, vp, vp, vp],
+    'mwx_pcg_amg': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp],
+}
+_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev'}
+
+ERRORS = {-1: 'MWX_E_BADARG', -2: 'MWX_E_CAPACITY', -3: 'MWX_E_NOCONV', -4: 'MWX_E_NOMEM'}
+
+
+class MwxError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MwxError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                "(nvcc, sm_100a). fem_forth_perturb_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = None if name in _VOID else ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what=''):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise MwxError(f"{what}: {ERRORS.get(rc, rc)}")
+    raise MwxError(f"{what}: cudaError {rc}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise MwxError("fem_forth_perturb_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / numpy array; None -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, 'data_ptr'):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
+def stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,57 @@
+// Device building blocks of hot path B shared by the Jacobi- and AMG-preconditioned CG drivers.
+#pragma once
+#include "common.cuh"
+
+namespace mwx {
+
+// Scalars of one CG solve, resident in device memory so that kernels chain without host round trips.
+struct CgScalars {
+    double rho;        // r . z of the current iteration
+    double rho_prev;   // r . z of the previous iteration
+    double pq;         // p . A p
+    double rr;         // r . r
+    double aux;        // scratch dot
+    unsigned int ticket[4];   // "last block done" counters, one per reduction site
+};
+
+constexpr int RED_MAX_BLOCKS = 4096;   // partial-sum slots per reduction site
+
+// y = A x (CSR, int64 indptr, int32 cols, fp64).  If dot_with != nullptr also accumulates
+// sum_i dot_with[i] * y[i] into *dot_out deterministically (per-CTA partials, last CTA folds them in
+// index order).  partials: RED_MAX_BLOCKS doubles, ticket: zero-initialised counter.
+int launch_spmv(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                const double *x, double *y, const double *dot_with, double *dot_out, double *partials,
+                unsigned int *ticket, cudaStream_t st);
+
+// y = c - A x (sign < 0) or y = c + A x (sign > 0); c may alias y.
+int launch_spmv_axpy(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                     const double *x, double *y, const double *c, int sign, cudaStream_t st);
+
+// One polynomial-smoother step: d = c1 d + c2 dinv (b - A x_in);  x_out = x_in + d  (x_out != x_in).
+int launch_smoother_step(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                         const double *x_in, double *x_out, const double *b, const double *dinv, double *d,
+                         double c1, double c2, cudaStream_t st);
+
+// r = b - A x, and (deterministic) rr = r.r, rho = sum dinv_i r_i^2 (dinv may be nullptr -> rho = rr).
+int launch_residual(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                    const double *x, const double *b, double *r, const double *dinv, CgScalars *sc,
+                    double *partials, cudaStream_t st);
+
+// diag[i] = A[i,i] (invert != 0: its reciprocal).
+int launch_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                        double *diag, int invert, cudaStream_t st);
+
+// out = sum a_i b_i (deterministic).
+int launch_dot(int64_t n, const double *a, const double *b, double *out, double *partials,
+               unsigned int *ticket, cudaStream_t st);
+
+// z = M^-1 r launcher used by cg_solve (nullptr = Jacobi / identity handled inside the vector kernels).
+typedef int (*PrecondFn)(void *ctx, const double *r, double *z, cudaStream_t st);
+
+// Preconditioned CG with scipy 1.4.1 `cg` semantics.  r, z, p, q: n-vectors of workspace.
+int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+             const double *b, double *x, double tol, int64_t maxiter, const double *dinv,
+             PrecondFn precond, void *ctx, double *r, double *z, double *p, double *q,
+             int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st);
+
+}  // namespace mwx

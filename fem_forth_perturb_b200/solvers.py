@@ -1,0 +1,308 @@
+"""Drop-in solver layer: the reference's ``utils.py`` call shapes on top of the device kernels.
+
+Mirrors ref main/example1/utils.py:
+  ``solver_iter_krylov`` / ``solver_iter_pcg`` (:265-320), ``solver_iter_krylov_iter`` (:212-263),
+  ``solver_iter_mgcg`` (:127-166), ``solver_iter_mgcg_iter`` (:87-125), ``build_pc_diag`` (:48-50),
+  ``solve`` (:326-368), ``condense`` (:384-460).
+Every factory returns a closure ``solver(A, b, **kw) -> x`` (numpy) that the reference's ``solve()``
+accepts unchanged; the closures additionally expose ``solver.solve_with_info(A, b) -> (x, iters)`` and
+``solver.last`` (iterations, info, residual, setup/solve seconds).  Same kwargs (``tol``, ``maxiter``,
+``Precondition``, ``verbose``), same ``"... total interation steps: N"`` print in the ``_iter`` flavours,
+same ``warnings.warn("Convergence not achieved!")``.  A user-supplied ``M`` / ``krylov`` callable cannot
+run on the device and raises (no CPU fallback).
+"""
+import ctypes
+import time
+import warnings
+
+import numpy as np
+
+from . import _lib as L
+from .assembly import DeviceCSR
+
+
+# ------------------------------------------------------------------ helpers
+def _to_device_csr(A):
+    return A if isinstance(A, DeviceCSR) else DeviceCSR.from_scipy(A)
+
+
+def _to_device_vec(b, device):
+    torch = L.require_cuda()
+    if isinstance(b, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(device)
+    return b.to(device=device, dtype=torch.float64).contiguous()
+
+
+class AMGHierarchy:
+    """``pyamg.ruge_stuben_solver(A)`` (host C++ setup, timed) uploaded once to the device.
+
+    mode: 'parity' = symmetric lexicographic Gauss-Seidel (pyamg's default; iteration-count parity),
+          'chebyshev' = Chebyshev(degree) smoothing (fast), 'jacobi' = 2 damped Jacobi steps (fast).
+    """
+    MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2}
+
+    def __init__(self, A, mode='parity', degree=3, theta=0.25, max_levels=10, max_coarse=10):
+        torch = L.require_cuda()
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {list(self.MODES)}")
+        lib = L.lib()
+        A = _to_device_csr(A)
+        self.n, self.mode = A.shape[0], mode
+        t0 = time.perf_counter()
+        ip = np.ascontiguousarray(A.d_indptr.cpu().numpy(), dtype=np.int64)
+        ix = np.ascontiguousarray(A.d_indices.cpu().numpy(), dtype=np.int32)
+        va = np.ascontiguousarray(A.d_data.cpu().numpy(), dtype=np.float64)
+        self._host = ctypes.c_void_p()
+        L.check(lib.mwx_amg_setup_host(self.n, L.ptr(ip), L.ptr(ix), L.ptr(va), float(theta), int(max_levels),
+                                       int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_host')
+        self.levels = lib.mwx_amg_num_levels(self._host)
+        self.setup_host_seconds = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        # coarsest level: dense pseudo-inverse (scipy 1.4.1 pinv2 semantics) through LAPACK
+        Ac = self.level_matrix(self.levels - 1, 0).toarray()
+        u, s, vh = np.linalg.svd(Ac, full_matrices=False)
+        rank = int(np.sum(s > 1e6 * np.finfo(np.float64).eps * s.max())) if s.size else 0
+        pinv = np.ascontiguousarray(((u[:, :rank] / s[:rank]) @ vh[:rank]).T)
+        self._dev = ctypes.c_void_p()
+        L.check(lib.mwx_amg_upload(self._host, self.MODES[mode], int(degree), L.ptr(pinv),
+                                   ctypes.byref(self._dev), L.stream()), 'mwx_amg_upload')
+        torch.cuda.synchronize()
+        self.upload_seconds = time.perf_counter() - t1
+
+    def level_dims(self, level, which=0):
+        dims = np.zeros(3, dtype=np.int64)
+        L.check(L.lib().mwx_amg_level_dims(self._host, level, which, L.ptr(dims)), 'mwx_amg_level_dims')
+        return tuple(int(v) for v in dims)
+
+    def level_matrix(self, level, which=0):
+        """scipy copy of A_l (which=0), P_l (1) or R_l (2) - for tests and diagnostics."""
+        import scipy.sparse as sp
+        rows, cols, nnz = self.level_dims(level, which)
+        ip = np.empty(rows + 1, np.int64); ix = np.empty(nnz, np.int32); va = np.empty(nnz, np.float64)
+        L.check(L.lib().mwx_amg_level_copy(self._host, level, which, L.ptr(ip), L.ptr(ix), L.ptr(va)),
+                'mwx_amg_level_copy')
+        return sp.csr_matrix((va, ix, ip), shape=(rows, cols))
+
+    def splitting(self, level):
+        rows = self.level_dims(level, 0)[0]
+        s = np.empty(rows, np.int32)
+        L.check(L.lib().mwx_amg_level_splitting(self._host, level, L.ptr(s)), 'mwx_amg_level_splitting')
+        return s
+
+    def level_sizes(self):
+        return [self.level_dims(l, 0)[0] for l in range(self.levels)]
+
+    def operator_complexity(self):
+        return sum(self.level_dims(l, 0)[2] for l in range(self.levels)) / self.level_dims(0, 0)[2]
+
+    def precondition(self, r):
+        """z = M^-1 r (one V(1,1) cycle) - ``ml.aspreconditioner()``."""
+        torch = L.require_cuda()
+        is_np = isinstance(r, np.ndarray)
+        rd = _to_device_vec(r, torch.device('cuda', torch.cuda.current_device()))
+        z = torch.empty_like(rd)
+        L.check(L.lib().mwx_amg_vcycle(self._dev, L.ptr(rd), L.ptr(z), L.stream()), 'mwx_amg_vcycle')
+        return z.cpu().numpy() if is_np else z
+
+    def __del__(self):
+        try:
+            lib = L.lib()
+            if getattr(self, '_dev', None):
+                lib.mwx_amg_destroy_dev(self._dev)
+            if getattr(self, '_host', None):
+                lib.mwx_amg_destroy_host(self._host)
+        except Exception:
+            pass
+
+
+def _run_pcg(A, b, tol, maxiter, precondition=True, amg=None):
+    """Device PCG; returns (x torch, iters, info, resid)."""
+    torch = L.require_cuda()
+    A = _to_device_csr(A)
+    n = A.shape[0]
+    dev = A.d_data.device
+    bd = _to_device_vec(b, dev)
+    x = torch.empty(n, dtype=torch.float64, device=dev)
+    work = torch.empty(4 * n, dtype=torch.float64, device=dev)
+    iters, info, resid = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_double(0.0)
+    mi = 0 if maxiter is None else int(maxiter)
+    if amg is None:
+        rc = L.lib().mwx_pcg_jacobi(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd), L.ptr(x),
+                                    float(tol), mi, 1 if precondition else 0, L.ptr(work), ctypes.byref(iters),
+                                    ctypes.byref(info), ctypes.byref(resid), L.stream())
+    else:
+        rc = L.lib().mwx_pcg_amg(amg._dev, n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd),
+                                 L.ptr(x), float(tol), mi, L.ptr(work), ctypes.byref(iters), ctypes.byref(info),
+                                 ctypes.byref(resid), L.stream())
+    if rc not in (0, -3):                       # -3 = MWX_E_NOCONV (breakdown): reported through info
+        L.check(rc, 'mwx_pcg')
+    return x, int(iters.value), int(info.value), float(resid.value)
+
+
+def _reject_host_callables(kwargs):
+    if kwargs.get('M') is not None:
+        raise NotImplementedError("a user-supplied preconditioner M is a host callable; the device path "
+                                  "offers Precondition=True (Jacobi) or solver_iter_mgcg (AMG). No CPU fallback.")
+
+
+def _finish(x, b, info, verbose, name, kwargs):
+    if info > 0:
+        warnings.warn("Convergence not achieved!")
+    elif info == 0 and verbose:
+        print(f"{name} converged to tol={kwargs.get('tol', 'default')} and atol={kwargs.get('atol', 'default')}")
+    return x.cpu().numpy() if isinstance(b, np.ndarray) else x
+
+
+# ------------------------------------------------------------------ factories (reference call shapes)
+def build_pc_diag(A):
+    """Diagonal preconditioner (ref utils.py:48-50): returns 1/diag(A) as a vector."""
+    return 1.0 / _to_device_csr(A).diagonal()
+
+
+def _make_krylov(print_iters, krylov=None, verbose=False, **kwargs):
+    if krylov is not None and getattr(krylov, '__name__', 'cg') != 'cg':
+        raise NotImplementedError("only conjugate gradients (scipy's cg) has a device implementation")
+
+    def run(A, b, **solve_time_kwargs):
+        kwargs.update(solve_time_kwargs)
+        kw = dict(kwargs)
+        pre = bool(kw.pop('Precondition', False)) is True
+        _reject_host_callables(kw)
+        t0 = time.perf_counter()
+        x, it, info, resid = _run_pcg(A, b, kw.get('tol', 1e-5), kw.get('maxiter'), precondition=pre)
+        solver.last = dict(iters=it, info=info, resid=resid, solve_seconds=time.perf_counter() - t0)
+        if print_iters:
+            print('cg', 'total interation steps:', it)
+        return _finish(x, b, info, verbose, 'cg', kw), it
+
+    def solver(A, b, **kw):
+        return run(A, b, **kw)[0]
+
+    solver.solve_with_info = run
+    solver.last = None
+    return solver
+
+
+def solver_iter_krylov(krylov=None, verbose=False, **kwargs):
+    """ref utils.py:265-316.  ``Precondition=True`` -> Jacobi (``build_pc_diag``) preconditioned CG."""
+    return _make_krylov(False, krylov, verbose, **kwargs)
+
+
+def solver_iter_krylov_iter(krylov=None, verbose=False, **kwargs):
+    """ref utils.py:212-263: same, and prints ``cg total interation steps: N``."""
+    return _make_krylov(True, krylov, verbose, **kwargs)
+
+
+def solver_iter_pcg(**kwargs):
+    """ref utils.py:318-320."""
+    return solver_iter_krylov(**kwargs)
+
+
+def _make_mgcg(print_iters, krylov=None, verbose=False, mode='parity', degree=3, **kwargs):
+    if krylov is not None and getattr(krylov, '__name__', 'cg') != 'cg':
+        raise NotImplementedError("only conjugate gradients (scipy's cg) has a device implementation")
+
+    def run(A, b, **solve_time_kwargs):
+        kwargs.update(solve_time_kwargs)
+        kw = dict(kwargs)
+        _reject_host_callables(kw)
+        A_d = _to_device_csr(A)
+        t0 = time.perf_counter()
+        ml = AMGHierarchy(A_d, mode=mode, degree=degree)          # rebuilt per solve, like the reference
+        t1 = time.perf_counter()
+        x, it, info, resid = _run_pcg(A_d, b, kw.get('tol', 1e-5), kw.get('maxiter'), amg=ml)
+        solver.last = dict(iters=it, info=info, resid=resid, setup_seconds=t1 - t0,
+                           solve_seconds=time.perf_counter() - t1, levels=ml.level_sizes(), mode=mode)
+        if print_iters:
+            print('mgcg total interation steps:', it)
+        return _finish(x, b, info, verbose, 'cg', kw), it
+
+    def solver(A, b, **kw):
+        return run(A, b, **kw)[0]
+
+    solver.solve_with_info = run
+    solver.last = None
+    return solver
+
+
+def solver_iter_mgcg(krylov=None, verbose=False, mode='parity', degree=3, **kwargs):
+    """ref utils.py:127-166: RS-AMG V-cycle preconditioned CG.  ``mode`` selects the smoother
+    ('parity' = pyamg's symmetric Gauss-Seidel, 'chebyshev' / 'jacobi' = fast device smoothers)."""
+    return _make_mgcg(False, krylov, verbose, mode, degree, **kwargs)
+
+
+def solver_iter_mgcg_iter(krylov=None, verbose=False, mode='parity', degree=3, **kwargs):
+    """ref utils.py:87-125: same, and prints ``mgcg total interation steps: N``."""
+    return _make_mgcg(True, krylov, verbose, mode, degree, **kwargs)
+
+
+# ------------------------------------------------------------------ solve / condense
+def solve(A, b, x=None, I=None, solver=None, **kwargs):
+    """ref utils.py:326-368 (linear systems only)."""
+    if solver is None:
+        raise NotImplementedError("the device path has no direct solver; pass solver_iter_pcg/mgcg (no CPU fallback)")
+    if x is not None and I is not None:
+        y = x.copy()
+        y[I] = solver(A, b, **kwargs)
+        return y
+    return solver(A, b, **kwargs)
+
+
+def _flatten_dofs(S):
+    if S is None:
+        return None
+    if isinstance(S, np.ndarray):
+        return S
+    if hasattr(S, 'flatten') and not isinstance(S, dict):
+        return S.flatten()
+    if isinstance(S, dict):
+        return np.unique(np.concatenate([S[k].flatten() for k in S]))
+    raise NotImplementedError("Unable to flatten the given set of DOFs.")
+
+
+def condense(A, b=None, x=None, I=None, D=None, expand=True):
+    """ref utils.py:384-460 on the device: ``Aout = A[I].T[I].T``, ``bout = b[I] - A[I].T[D].T @ x[D]``.
+    ``A`` may be a DeviceCSR (stays in HBM) or a scipy matrix (uploaded)."""
+    torch = L.require_cuda()
+    D, I = _flatten_dofs(D), _flatten_dofs(I)
+    A = _to_device_csr(A)
+    n = A.shape[0]
+    if x is None:
+        x = np.zeros(n)
+    if I is None and D is None:
+        raise Exception("Either I or D must be given!")
+    if I is not None and D is not None:
+        raise Exception("Give only I or only D!")
+    keep_h = np.zeros(n, dtype=np.int32)
+    if I is None:
+        keep_h[:] = 1
+        keep_h[D] = 0
+        I = np.nonzero(keep_h)[0]
+    else:
+        keep_h[I] = 1
+    dev = A.d_data.device
+    keep = torch.from_numpy(keep_h).to(dev)
+    newid = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    indptr_out = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    n_out, nnz_out = ctypes.c_int64(0), ctypes.c_int64(0)
+    lib, st = L.lib(), L.stream()
+    L.check(lib.mwx_condense_count(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(keep), L.ptr(newid),
+                                   L.ptr(indptr_out), ctypes.byref(n_out), ctypes.byref(nnz_out), st),
+            'mwx_condense_count')
+    no, nz = int(n_out.value), int(nnz_out.value)
+    indices_out = torch.empty(nz, dtype=torch.int32, device=dev)
+    values_out = torch.empty(nz, dtype=torch.float64, device=dev)
+    have_b = b is not None
+    if have_b and not isinstance(b, (np.ndarray,)) and not hasattr(b, 'data_ptr'):
+        raise NotImplementedError("condense: generalized eigenproblems (matrix b) are not on the device path")
+    bd = _to_device_vec(b, dev) if have_b else None
+    xd = _to_device_vec(x, dev) if have_b else None
+    b_out = torch.empty(no, dtype=torch.float64, device=dev) if have_b else None
+    L.check(lib.mwx_condense_fill(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(keep),
+                                  L.ptr(newid), L.ptr(indptr_out), L.ptr(indices_out), L.ptr(values_out),
+                                  L.ptr(bd), L.ptr(xd), L.ptr(b_out), st), 'mwx_condense_fill')
+    Aout = DeviceCSR(indptr_out[:no + 1].contiguous(), indices_out, values_out, (no, no))
+    ret = (Aout,) if not have_b else (Aout, b_out.cpu().numpy() if isinstance(b, np.ndarray) else b_out)
+    if expand:
+        ret += (x, I)
+    return ret if len(ret) > 1 else ret[0]

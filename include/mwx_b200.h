@@ -1,0 +1,188 @@
+/* mwx_b200.h - C ABI of libmwx_b200.so: the B200 (sm_100a) drop-in for the two data-parallel hot
+ * paths of YerbaPage/FEM_forth_perturb.
+ *
+ * The reference is pure Python over un-vendored scikit-fem 2.1.1 / scipy 1.4.1 / pyamg 4.0.0 and
+ * has no FFI of its own.  Each entry point below names the reference call
+ * (file:line under /root/reference) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * stub a maintainer would add to main/example1/utils.py / run.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return value: 0 = ok, <0 = MWX_E_* (bad argument / capacity), >0 = cudaError_t;
+ *  - no global state, no exceptions, re-entrant per set of buffers;
+ *  - mesh arrays are structure-of-arrays: t = [t0 | t1 | t2] (3*nt int32), facets = [f0 | f1],
+ *    t2f = [e0 | e1 | e2], coordinates pxy = interleaved (x,y) pairs (2*nv doubles);
+ *  - CSR: indptr int64 (N+1), indices int32, values fp64.  (scipy-compatible after a dtype cast;
+ *    int64 indptr is what makes the 8k x 8k mesh, nnz = 3.09e9, addressable.)
+ */
+#ifndef MWX_B200_H
+#define MWX_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWX_E_BADARG   (-1)
+#define MWX_E_CAPACITY (-2)   /* a per-row / per-vertex local capacity was exceeded        */
+#define MWX_E_NOCONV   (-3)   /* iteration limit reached (result still written)           */
+#define MWX_E_NOMEM    (-4)
+
+int mwx_version(void);
+
+/* ------------------------------------------------------------------ mesh  (hot path A, setup)
+ * Replaces skfem MeshTri._build_mappings / refine reached from
+ *   ref main/example1/run.py:508 (MeshTri()), :512 (m.refine()).                              */
+
+/* Sort every column of t ascending (in place). */
+int mwx_mesh_sort_columns(int64_t nt, int32_t *t, void *stream);
+
+/* Entity -> element incidence (CSR) of a (ndof_per_elem x nt) SoA connectivity:
+ * inc_ptr (nent+1), inc_idx (ndof_per_elem*nt) holding codes (element << 3 | local index),
+ * ascending inside each entity.  Used for vertex->triangle and DOF->triangle maps. */
+int mwx_incidence(int64_t nent, int64_t nt, int32_t ndof_per_elem, const int32_t *conn,
+                  int64_t *inc_ptr, int32_t *inc_idx, void *stream);
+
+/* Facets = lexicographically sorted unique (min,max) vertex pairs.  Pass 1 fills fstart (nv+1):
+ * facets whose smaller vertex is a are numbered fstart[a] .. fstart[a+1]-1, and returns nf. */
+int mwx_mesh_facets_count(int64_t nv, int64_t nt, const int32_t *t, const int64_t *v2t_ptr,
+                          const int32_t *v2t_idx, int64_t *fstart, int64_t *nf_host, void *stream);
+/* Pass 2 writes facets (2*nf) and t2f (3*nt; local edges (0,1),(1,2),(0,2)). */
+int mwx_mesh_facets_fill(int64_t nv, int64_t nt, const int32_t *t, const int64_t *v2t_ptr,
+                         const int32_t *v2t_idx, const int64_t *fstart, int64_t nf,
+                         int32_t *facets, int32_t *t2f, void *stream);
+
+/* Uniform (red) refinement: vertex nv+j = midpoint of facet j; children in skfem's block order
+ * (t0,m01,m02),(t1,m01,m12),(t2,m02,m12),(m01,m12,m02), columns sorted.  Outputs: pxy_new
+ * (2*(nv+nf)), t_new (3*4*nt). */
+int mwx_mesh_refine(int64_t nv, int64_t nt, int64_t nf, const double *pxy, const int32_t *t,
+                    const int32_t *facets, const int32_t *t2f, double *pxy_new, int32_t *t_new,
+                    void *stream);
+
+/* Morley / P2 element_dofs (6*nt): rows 0-2 = t, rows 3-5 = nv + t2f  (skfem Dofs). */
+int mwx_element_dofs(int64_t nv, int64_t nt, const int32_t *t, const int32_t *t2f,
+                     int32_t *edofs, void *stream);
+
+/* Boundary facets: count of elements per facet == 1.  facet_count (nf) int32 output. */
+int mwx_facet_element_count(int64_t nf, int64_t nt, const int32_t *t2f, int32_t *facet_count,
+                            void *stream);
+
+/* ------------------------------------------------------------------ CSR pattern + slot map
+ * Replaces scipy coo_matrix(...).tocsr() reached from skfem BilinearForm.assemble
+ *   ref main/example1/run.py:210 (asm(a_load, basis['u']) + asm(b_load, basis['u'])).
+ * Pass 1: row lengths -> indptr (N+1), returns nnz and the longest row. */
+int mwx_pattern_count(int64_t ndofs, int64_t nt, const int32_t *edofs, const int64_t *r2e_ptr,
+                      const int32_t *r2e_idx, int64_t *indptr, int64_t *nnz_host,
+                      int32_t *max_row_host, void *stream);
+/* Pass 2: indices (nnz, ascending per row) and the slot map: for pair p of r2e_idx (row r, element e)
+ * slot8[8*p + j] = position of column edofs[j][e] inside row r (j = 0..5; bytes 6,7 unused). */
+int mwx_pattern_fill(int64_t ndofs, int64_t nt, const int32_t *edofs, const int64_t *r2e_ptr,
+                     const int32_t *r2e_idx, const int64_t *indptr, int32_t *indices,
+                     uint8_t *slot8, void *stream);
+
+/* ------------------------------------------------------------------ Morley element kernel (hot)
+ * values[k] = ca * (hess u : hess v) + cb * (grad u . grad v), summed over elements in ascending
+ * element order per CSR slot (deterministic, no atomics).  Replaces
+ *   K2 = epsilon**2 * asm(a_load, basis['u']) + asm(b_load, basis['u'])   ref main/example1/run.py:210
+ * (a_load/b_load: ref main/example1/run.py:110-123).  accumulate != 0 adds into values. */
+int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy, const int32_t *t,
+                        const int64_t *r2e_ptr, const int32_t *r2e_idx, const uint8_t *slot8,
+                        const int64_t *indptr, double ca, double cb, int32_t accumulate,
+                        double *values, void *stream);
+
+/* Boundary-facet (Nitsche penalty) terms, ref main/example1/run.py:134-146,253-260:
+ * values += c1*penalty_1 + c2*penalty_2 + c3*penalty_3(sigma) over nbf boundary facets (FacetBasis:
+ * 3-point Gauss rule, w.n = outward unit normal, w.h = facet length).  btri[b] = owning triangle,
+ * blocal[b] = local edge (0,1,2) of the facet in it.  Gather form, like the interior kernel: one
+ * thread per touched matrix row rows[r] walks pair_code[pair_ptr[r] .. pair_ptr[r+1]) = (b << 3 | i)
+ * in ascending order and adds row i of facet b's 6x6 matrix - fixed order, no atomics, O(sqrt N). */
+int mwx_assemble_penalty(int64_t nt, int64_t nbf, const double *pxy, const int32_t *t,
+                         const int32_t *edofs, const int32_t *btri, const int32_t *blocal,
+                         int64_t nrows, const int32_t *rows, const int64_t *pair_ptr,
+                         const int32_t *pair_code, const int64_t *indptr, const int32_t *indices,
+                         double c1, double c2, double c3, double sigma, double *values, void *stream);
+
+/* values_out = alpha * a + beta * b  (same pattern; scipy's `eps**2 * A + B`). */
+int mwx_axpby(int64_t n, double alpha, const double *a, double beta, const double *b,
+              double *out, void *stream);
+
+/* ------------------------------------------------------------------ condense (glue A -> B)
+ * Replaces condense(K2, f2, D=...) ref main/example1/utils.py:384-460:
+ *   Aout = A[I].T[I].T,  bout = b[I] - A[I].T[D].T @ x[D].
+ * keep (N) int32 0/1 mask of I; newid (N+1) int32 = exclusive scan of keep (output of pass 1);
+ *   indptr_out must hold N+1 entries (n_out is only known after pass 1). */
+int mwx_condense_count(int64_t n, const int64_t *indptr, const int32_t *indices,
+                       const int32_t *keep, int32_t *newid, int64_t *indptr_out,
+                       int64_t *n_out_host, int64_t *nnz_out_host, void *stream);
+int mwx_condense_fill(int64_t n, const int64_t *indptr, const int32_t *indices,
+                      const double *values, const int32_t *keep, const int32_t *newid,
+                      const int64_t *indptr_out, int32_t *indices_out, double *values_out,
+                      const double *b, const double *x, double *b_out, void *stream);
+
+/* ------------------------------------------------------------------ SpMV / vector kernels (hot path B)
+ * y = A x.  Replaces scipy csr_matvec inside spl.cg  ref main/example1/utils.py:157. */
+int mwx_spmv(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+             const double *x, double *y, void *stream);
+/* diag[i] = A[i,i] (0 if absent): build_pc_diag, ref main/example1/utils.py:48-50. */
+int mwx_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices,
+                     const double *values, double *diag, void *stream);
+
+/* Jacobi-preconditioned CG with scipy-1.4.1 `cg` stopping semantics:
+ *   solver_iter_krylov(Precondition=True) / solver_iter_pcg   ref main/example1/utils.py:265-320.
+ * work: 5*n doubles.  info_host[0] = 0 converged / maxiter not converged; iters_host = iterations;
+ * resid_host = final ||r||_2.  precondition = 0 runs plain CG (M = I). */
+int mwx_pcg_jacobi(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                   const double *b, double *x, double tol, int64_t maxiter, int32_t precondition,
+                   double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
+                   void *stream);
+
+/* ------------------------------------------------------------------ AMG (hot path B)
+ * Host setup = pyamg.ruge_stuben_solver(A) ref main/example1/utils.py:154 (classical strength 0.25,
+ * first-pass RS splitting, direct interpolation, Galerkin RAP, <=10 levels, coarse <=10 rows).
+ * All arrays here are HOST pointers.  Opaque hierarchy; query level sizes then copy out. */
+typedef struct mwx_amg_host mwx_amg_host_t;
+int mwx_amg_setup_host(int64_t n, const int64_t *indptr_host, const int32_t *indices_host,
+                       const double *values_host, double theta, int32_t max_levels,
+                       int32_t max_coarse, mwx_amg_host_t **out);
+int mwx_amg_num_levels(const mwx_amg_host_t *h);
+/* which: 0 = A_l, 1 = P_l (n_l x n_{l+1}), 2 = R_l (n_{l+1} x n_l).  dims_host = {rows, cols, nnz}. */
+int mwx_amg_level_dims(const mwx_amg_host_t *h, int32_t level, int32_t which, int64_t *dims_host);
+int mwx_amg_level_copy(const mwx_amg_host_t *h, int32_t level, int32_t which, int64_t *indptr_host,
+                       int32_t *indices_host, double *values_host);
+/* C/F splitting of level `level` (1 = C) for tests. */
+int mwx_amg_level_splitting(const mwx_amg_host_t *h, int32_t level, int32_t *split_host);
+void mwx_amg_destroy_host(mwx_amg_host_t *h);
+
+/* Dependency levels of the lexicographic Gauss-Seidel sweep of a CSR matrix (host): row i is in
+ * wavefront 1 + max(wavefront(j) : j < i, a_ij != 0).  order_host (n) lists rows grouped by
+ * wavefront, wave_ptr_host (nwaves+1).  Returns nwaves through nwaves_host. */
+int mwx_gs_wavefronts_host(int64_t n, const int64_t *indptr_host, const int32_t *indices_host,
+                           int32_t *order_host, int64_t *wave_ptr_host, int64_t *nwaves_host);
+/* Same for the backward sweep (row i waits for its neighbours j > i). */
+int mwx_gs_wavefronts_backward_host(int64_t n, const int64_t *indptr_host, const int32_t *indices_host,
+                                    int32_t *order_host, int64_t *wave_ptr_host, int64_t *nwaves_host);
+
+/* Device V-cycle preconditioner (ml.aspreconditioner(), ref main/example1/utils.py:155). */
+typedef struct mwx_amg_dev mwx_amg_dev_t;
+/* smoother: 0 = exact lexicographic symmetric Gauss-Seidel (parity mode, wavefront-scheduled),
+ *           1 = Chebyshev(degree) on D^-1 A (fast mode), 2 = damped Jacobi x2 (fast mode). */
+/* coarse_pinv_host: dense row-major pseudo-inverse of the coarsest A (scipy pinv2 in the reference);
+ * NULL = computed inside by a symmetric Jacobi eigen-solver with pinv2's cutoff. */
+int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t cheby_degree,
+                   const double *coarse_pinv_host, mwx_amg_dev_t **out, void *stream);
+/* Estimated spectral radius of D^-1 A on a level (fast-mode smoothers; 0 in parity mode). */
+int mwx_amg_level_rho(const mwx_amg_dev_t *d, int32_t level, double *rho_host);
+void mwx_amg_destroy_dev(mwx_amg_dev_t *d);
+/* z = M^-1 r : one V(1,1) cycle from a zero initial guess. */
+int mwx_amg_vcycle(mwx_amg_dev_t *d, const double *r, double *z, void *stream);
+/* AMG-preconditioned CG, scipy-1.4.1 stopping semantics: solver_iter_mgcg ref utils.py:127-166. */
+int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_t *indices,
+                const double *values, const double *b, double *x, double tol, int64_t maxiter,
+                double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
+                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MWX_B200_H */

@@ -1,0 +1,159 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, the C++ AMG setup reproduces the oracle hierarchy, and nothing falls back to the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import fem_forth_perturb_b200 as F
+from fem_forth_perturb_b200 import _lib as L
+from conftest import ROOT
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, 'include', 'mwx_b200.h')).read()
+    return sorted(set(re.findall(r'^(?:int|void)\s+(mwx_\w+)\s*\(', txt, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/mwx_b200.h but not exported'
+        assert n in L._SIGNATURES, f'{n} has no ctypes signature'
+    assert lib.mwx_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(F.MwxError):
+        F.MeshTri()
+    with pytest.raises(F.MwxError):
+        F.solver_iter_pcg(tol=1e-8)(sp.identity(4, format='csr'), np.ones(4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'fem_forth_perturb_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+                assert 'oracle/' not in src.replace('oracle/scipy_cg.py', ''), fn
+
+
+def test_form_dispatch_is_by_name_and_rejects_unknown():
+    f = 1e-4 * F.a_load + F.b_load
+    assert f.terms == {'a_load': 1e-4, 'b_load': 1.0} and f.kind == 'interior'
+
+    def a_load(u, v, w):          # a function named like the reference's form
+        return None
+    assert F.as_form(a_load).terms == {'a_load': 1.0}
+
+    class SkfemLike:              # skfem BilinearForm keeps the python function in .form
+        def __init__(self, fn):
+            self.form = fn
+    assert F.as_form(SkfemLike(a_load)).terms == {'a_load': 1.0}
+
+    def mass(u, v, w):
+        return None
+    with pytest.raises(NotImplementedError):
+        F.as_form(mass)
+    with pytest.raises(NotImplementedError):
+        (F.a_load + F.penalty_1).kind
+
+
+def _k2c(level, eps):
+    from oracle.skfem_mesh import MeshTri
+    from oracle import pipeline as pl
+    m = MeshTri()
+    m.refine(level)
+    S = pl.solve_problem(m, pl.Ex1(eps), wkind='P1', intorder=5, return_system=True)
+    K = S['Kc']
+    K.sort_indices()
+    return K, S['bc']
+
+
+def _native_levels(K):
+    lib = L.lib()
+    ip, ix, va = K.indptr.astype(np.int64), K.indices.astype(np.int32), K.data.astype(np.float64)
+    h = ctypes.c_void_p()
+    L.check(lib.mwx_amg_setup_host(K.shape[0], L.ptr(ip), L.ptr(ix), L.ptr(va), 0.25, 10, 10, ctypes.byref(h)))
+    out = []
+    nl = lib.mwx_amg_num_levels(h)
+    for l in range(nl):
+        mats = []
+        for which in (0, 1, 2):
+            if which and l == nl - 1:
+                mats.append(None)
+                continue
+            dims = np.zeros(3, np.int64)
+            L.check(lib.mwx_amg_level_dims(h, l, which, L.ptr(dims)))
+            r, c, nnz = (int(v) for v in dims)
+            p = np.empty(r + 1, np.int64); j = np.empty(nnz, np.int32); v = np.empty(nnz)
+            L.check(lib.mwx_amg_level_copy(h, l, which, L.ptr(p), L.ptr(j), L.ptr(v)))
+            mats.append(sp.csr_matrix((v, j, p), shape=(r, c)))
+        split = None
+        if l < nl - 1:
+            split = np.empty(mats[0].shape[0], np.int32)
+            L.check(lib.mwx_amg_level_splitting(h, l, L.ptr(split)))
+        out.append((mats, split))
+    lib.mwx_amg_destroy_host(h)
+    return out
+
+
+@pytest.mark.parametrize('level,eps', [(2, 1.0), (4, 1.0), (5, 1e-2), (6, 1e-4)])
+def test_native_amg_setup_matches_oracle_hierarchy(level, eps):
+    """mwx_amg_setup_host (C++) vs the oracle's pyamg restatement: identical C/F splittings and
+    patterns on every level, operators equal to round-off."""
+    from oracle.pyamg_rs import RugeStuben
+    K, _ = _k2c(level, eps)
+    ml = RugeStuben(K)
+    nat = _native_levels(K)
+    assert [m[0][0].shape[0] for m in nat] == [a.shape[0] for a in ml.A]
+    for l, ((A, P, R), split) in enumerate(nat):
+        Ao = ml.A[l]
+        assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+        assert abs(A - Ao).max() <= 1e-13 * abs(Ao).max()
+        if split is not None:
+            assert np.array_equal(split, ml.split[l])
+            assert np.array_equal(P.indices, ml.P[l].indices)
+            assert abs(P - ml.P[l]).max() <= 1e-14
+            assert abs(R - ml.P[l].T).max() <= 1e-14
+
+
+def test_amg_setup_tiny_and_bad_arguments():
+    lib = L.lib()
+    K = sp.identity(5, format='csr')
+    nat = _native_levels(K)                       # n <= max_coarse: single level, no P
+    assert len(nat) == 1 and nat[0][0][1] is None
+    h = ctypes.c_void_p()
+    assert lib.mwx_amg_setup_host(0, None, None, None, 0.25, 10, 10, ctypes.byref(h)) == -1
+    assert lib.mwx_spmv(0, None, None, None, None, None, None) == -1
+    assert lib.mwx_pcg_jacobi(4, None, None, None, None, None, 1e-8, 0, 1, None, None, None, None, None) == -1
+
+
+def test_gs_wavefronts_respect_dependencies():
+    lib = L.lib()
+    K, _ = _k2c(4, 1.0)
+    n = K.shape[0]
+    ip, ix = K.indptr.astype(np.int64), K.indices.astype(np.int32)
+    for fn, backward in ((lib.mwx_gs_wavefronts_host, False), (lib.mwx_gs_wavefronts_backward_host, True)):
+        order = np.empty(n, np.int32); wp = np.zeros(n + 1, np.int64); nw = ctypes.c_int64(0)
+        L.check(fn(n, L.ptr(ip), L.ptr(ix), L.ptr(order), L.ptr(wp), ctypes.byref(nw)))
+        nw = nw.value
+        assert sorted(order.tolist()) == list(range(n)) and wp[nw] == n
+        wave = np.empty(n, np.int64)
+        for w in range(nw):
+            wave[order[wp[w]:wp[w + 1]]] = w
+        for i in range(n):
+            nb = ix[ip[i]:ip[i + 1]]
+            dep = nb[nb > i] if backward else nb[nb < i]
+            assert np.all(wave[dep] < wave[i])          # every dependency sits in an earlier wavefront
+            assert wave[i] == (wave[dep].max() + 1 if len(dep) else 0)
