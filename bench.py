@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py - the reference's hot path (MWX assembly -> condense -> SpMV -> AMG-PCG) on B200.
+
+One "step" = one pass of the hot path over the level-L unit-square mesh (default L = 12: 67 125 249
+Morley DOFs, nnz(K2) = 771 817 473 - BASELINE.json config "strong/weak scaling: >= 50M-DOF unit-square
+mesh"; config "assembly-only microbench" is the same mesh family, see --level):
+    assemble K2 = eps^2 A + B      (mwx_assemble_morley, one launch)
+    condense the Dirichlet DOFs    (mwx_condense_*)
+    one SpMV y = K2c x             (mwx_spmv; the roofline kernel)
+    one AMG-PCG solve K2c u = b    (mwx_pcg_amg, Chebyshev-smoothed V-cycle, tol 1e-8)
+Mesh refinement, CSR pattern / slot map and the AMG hierarchy are SETUP: built once, timed and
+reported separately (north_star: "hierarchy built once on the host as timed setup").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--level L] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+EPS = 1e-2            # eps^2 = 1e-4 (SURVEY 8d microbench setting)
+TOL = 1e-8            # the reference's tol (ref main/example1/run.py:20)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.samples, self.reasons, self.proc = [], set(), None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(',')]
+            try:
+                self.samples.append((float(parts[0]), float(parts[1])))
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': sorted(self.reasons), 'samples': 0}
+        sm = sorted(s[0] for s in self.samples)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(s[1] for s in self.samples),
+                'reasons': sorted(self.reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_pass(level, eps=EPS, tol=TOL):
+    """The reference's own CPU path, restated (oracle port: skfem asm + condense + pyamg RS + scipy-1.4.1 cg)
+    on a bounded level.  Returns phase seconds.  Only this function and the parity tests touch oracle/."""
+    from oracle.skfem_mesh import MeshTri as OMesh
+    from oracle.skfem_basis import InteriorBasis as OInterior
+    from oracle import skfem_asm as oa
+    from oracle.pyamg_rs import RugeStuben
+    from oracle.scipy_cg import cg141
+    m = OMesh().refine(level)
+    t0 = time.perf_counter()
+    ub = OInterior(m, 'Morley', 5)                                   # basis tabulation (part of skfem assembly)
+    K2 = eps ** 2 * oa.asm_bilinear(oa.a_load, ub) + oa.asm_bilinear(oa.b_load, ub)
+    t1 = time.perf_counter()
+    rng = np.random.default_rng(1234)
+    D = oa.easy_boundary(ub)
+    Kc, _, _, I = oa.condense(K2, np.zeros(K2.shape[0]), D=D)
+    xs = rng.uniform(-1, 1, Kc.shape[0])
+    b = Kc @ xs
+    t2 = time.perf_counter()
+    y = Kc @ xs
+    t3 = time.perf_counter()
+    ml = RugeStuben(Kc)
+    t4 = time.perf_counter()
+    x, info, its = cg141(Kc, b, M=ml.precondition, tol=tol, maxiter=1000)
+    t5 = time.perf_counter()
+    return dict(ndofs=K2.shape[0], n=Kc.shape[0], nnz=Kc.nnz, asm_s=t1 - t0, condense_s=t2 - t1, spmv_s=t3 - t2,
+                amg_setup_s=t4 - t3, pcg_s=t5 - t4, iters=its, info=info)
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU restatement of the reference path on the host cores (rank 0 only)."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    level = args.ref_level
+    res = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_pass(level)
+        if i >= args.warmup:
+            res.append(r)
+    step_s = float(np.mean([r['asm_s'] + r['condense_s'] + r['spmv_s'] + r['pcg_s'] for r in res]))
+    step_setup_s = step_s + float(np.mean([r['amg_setup_s'] for r in res]))
+    r0 = res[0]
+    value = r0['ndofs'] / step_s / 1e6
+    sample = (f"level {level} of the same mesh family ({r0['ndofs']} DOFs): asm(a_load)+asm(b_load) incl. basis "
+              f"tabulation, condense, 1 SpMV, RS-AMG(sym. GS)-PCG tol {TOL} ({r0['iters']} its); AMG setup "
+              f"({np.mean([r['amg_setup_s'] for r in res]):.2f} s) reported separately like the GPU arm")
+    line = {
+        'impl': 'reference', 'metric': 'hot_path_MDOF_per_s', 'value': value, 'unit': 'MDOF/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_s * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'MWX assemble+condense+SpMV+AMG-PCG, unit square level {level} (bounded CPU sample '
+                               f'of the level-{args.level} workload), eps={EPS}, tol={TOL}'},
+        'assembly_mdof_s': r0['ndofs'] / float(np.mean([r['asm_s'] for r in res])) / 1e6,
+        'pcg': {'s_per_solve': float(np.mean([r['pcg_s'] for r in res])), 'iters': r0['iters'],
+                'setup_s': float(np.mean([r['amg_setup_s'] for r in res])), 'mode': 'parity (symmetric GS)'},
+        'spmv_gbs': (12 * r0['nnz'] + 20 * r0['n']) / float(np.mean([r['spmv_s'] for r in res])) / 1e9,
+        'value_incl_amg_setup': r0['ndofs'] / step_setup_s / 1e6,
+        'cpu_baseline': {'value': value, 'unit': 'MDOF/s', 'cores': 1, 'kind': 'port', 'sample': sample,
+                         'host_cores_available': os.cpu_count()},
+        'e2e': {'value': value, 'unit': 'MDOF/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--level', type=int, default=12, help='refinements of the unit square (12 -> 67.1 M DOFs)')
+    ap.add_argument('--ref-level', type=int, default=8, help='bounded level for the CPU reference arm')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--mode', default='chebyshev', choices=['chebyshev', 'jacobi', 'parity'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import fem_forth_perturb_b200 as F
+    from fem_forth_perturb_b200 import _lib as L
+    dev = torch.device('cuda', local)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- setup (timed, not part of a step)
+    t0 = time.perf_counter()
+    gm = F.MeshTri().refine(args.level)
+    torch.cuda.synchronize()
+    t_mesh = time.perf_counter() - t0
+    basis = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+    t0 = time.perf_counter()
+    pat = basis.pattern()
+    torch.cuda.synchronize()
+    t_pattern = time.perf_counter() - t0
+    N, nt, nnz = basis.N, gm.nt, pat['nnz']
+    form = EPS ** 2 * F.a_load + F.b_load
+    # Dirichlet set of easy_boundary (ref main/example1/run.py:86-104): boundary vertices + boundary facets
+    bf = gm.boundary_facets()
+    D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+    K2 = F.asm_gpu(form, basis)
+    t0 = time.perf_counter()
+    plan = F.CondensePlan(K2, D=D)                 # kept-row numbering + condensed indptr: pattern-only, once
+    torch.cuda.synchronize()
+    t_cplan = time.perf_counter() - t0
+    Kc, _ = plan.apply(K2)
+    n, nnzc = Kc.shape[0], Kc.nnz
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xstar = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 2 - 1     # manufactured solution
+    b = Kc.dot(xstar)
+    t0 = time.perf_counter()
+    ml = F.AMGHierarchy(Kc, mode=args.mode, degree=3)
+    t_amg = time.perf_counter() - t0
+    from fem_forth_perturb_b200.solvers import _run_pcg
+    # pinned host inputs / outputs for the end-to-end leg
+    p_host = torch.empty(2 * gm.nv, dtype=torch.float64).pin_memory()
+    t_host = torch.empty(3 * gm.nt, dtype=torch.int32).pin_memory()
+    b_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    p_host.copy_(gm.d_pxy); t_host.copy_(gm.d_t); b_host.copy_(b)
+    torch.cuda.synchronize()
+    vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    vals_c = torch.empty(nnzc, dtype=torch.float64, device=dev)
+    ysp = torch.empty(n, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)     # 256 MiB > 126 MB L2
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(e2e):
+        """One pass of the hot path.  Returns per-phase device milliseconds and the iteration count."""
+        marks = [ev() for _ in range(6)]
+        if e2e:
+            gm.d_pxy.copy_(p_host, non_blocking=True)
+            gm.d_t.copy_(t_host, non_blocking=True)
+            bd = b_host.to(dev, non_blocking=True)
+        else:
+            bd = b
+        marks[0].record()
+        K = F.asm_gpu(form, basis, out=vals)
+        marks[1].record()
+        Kcs, _ = plan.apply(K, values_out=vals_c)
+        marks[2].record()
+        flush.zero_()                                   # evict the operator from L2 before the SpMV sample
+        marks[3].record()
+        L.check(L.lib().mwx_spmv(n, L.ptr(Kcs.d_indptr), L.ptr(Kcs.d_indices), L.ptr(Kcs.d_data), L.ptr(xstar),
+                                 L.ptr(ysp), L.stream()), 'mwx_spmv')
+        marks[4].record()
+        x, its, info, resid = _run_pcg(Kcs, bd, TOL, 2000, amg=ml)
+        marks[5].record()
+        if e2e:
+            x_host.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+        ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(5)]
+        return dict(asm=ms[0], condense=ms[1], spmv=ms[3], pcg=ms[4], its=its, info=info, resid=resid, x=x)
+
+    def timed(e2e, steps, warmup):
+        for _ in range(warmup):
+            step(e2e)
+        sync_all()
+        e0, e1 = ev(), ev()
+        e0.record()
+        rs = [step(e2e) for _ in range(steps)]
+        e1.record()
+        sync_all()
+        total_ms = e0.elapsed_time(e1)
+        if world > 1:
+            tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            total_ms = float(tmax.item())
+        return total_ms, rs
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, rs = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, rs_e2e = timed(True, args.steps, 1)
+
+    # solution check of the last solve (manufactured x*)
+    xerr = float(torch.linalg.norm(rs[-1]['x'] - xstar) / torch.linalg.norm(xstar))
+
+    def mean(key, rr=rs):
+        return float(np.mean([r[key] for r in rr]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    ms_step = total_ms / args.steps
+    units = N * world                                          # every rank runs its own level-L problem (weak)
+    value = units / (ms_step * 1e-3) / 1e6
+    spmv_bytes = 12 * nnzc + 20 * n                            # values 8 + col 4 per nnz; 20 B/row
+    asm_bytes = 308 * nt                                       # DESIGN.md section 4 (gather formulation)
+    spmv_gbs = spmv_bytes / (mean('spmv') * 1e-3) / 1e9
+    asm_gbs = asm_bytes / (mean('asm') * 1e-3) / 1e9
+    iters = rs[-1]['its']
+    # kernels launched per step (counted from the code paths above): assembly 1; condense 2 scans (3+3+..) + 2;
+    # spmv 1; PCG: per iteration 3 CG kernels + dot + V-cycle kernels
+    nlev = ml.levels
+    per_vcycle = (nlev - 1) * (1 + 2 + 1 + 1 + 1 + 3 + 1) + 1
+    gpu_launches = int(args.steps * (1 + 1 + 1 + 1 + 3 + iters * (4 + per_vcycle)))
+    line = {
+        'metric': 'hot_path_MDOF_per_s', 'value': value, 'unit': 'MDOF/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'MWX assemble+condense+SpMV+AMG-PCG, unit square level {args.level}: {N} Morley DOFs, '
+                               f'{nt} triangles, nnz(K2)={nnz}, condensed n={n}; eps={EPS}, tol={TOL}, rhs=K2c@x* '
+                               f'(x*~U(-1,1), seed 1234); AMG smoother={args.mode}',
+                   'l2': 'operator (9.3 GB) and vectors (0.5 GB each) exceed the 126 MB L2; a 256 MiB buffer is '
+                         'written before the SpMV sample'},
+        'assembly_mdof_s': N / (mean('asm') * 1e-3) / 1e6,
+        'assembly_ms': mean('asm'), 'condense_ms': mean('condense'),
+        'pcg': {'s_per_solve': mean('pcg') * 1e-3, 'iters': iters, 'info': rs[-1]['info'], 'mode': args.mode,
+                'ms_per_iter': mean('pcg') / max(iters, 1), 'rel_err_vs_manufactured': xerr,
+                'levels': ml.level_sizes(), 'operator_complexity': ml.operator_complexity()},
+        'spmv': {'ms': mean('spmv'), 'gbs': spmv_gbs, 'frac_of_peak': spmv_gbs / peak},
+        'setup_s': {'mesh_refine': t_mesh, 'pattern_slotmap': t_pattern, 'condense_plan': t_cplan, 'amg_host_rs': ml.setup_host_seconds,
+                    'amg_upload': ml.upload_seconds, 'amg_total': t_amg},
+        'roofline': {'kernel': 'k_spmv (CSR SpMV, fine level)', 'bound': 'hbm', 'achieved': spmv_gbs, 'peak': peak,
+                     'unit': 'GB/s', 'frac': spmv_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes': spmv_bytes},
+        'roofline_assembly': {'kernel': 'k_assemble_morley', 'bound': 'hbm', 'achieved': asm_gbs, 'peak': peak,
+                              'unit': 'GB/s', 'frac': asm_gbs / peak, 'traffic': None,
+                              'algorithmic_bytes': asm_bytes},
+        'e2e': {'value': units / (e2e_ms / args.steps * 1e-3) / 1e6, 'unit': 'MDOF/s',
+                'h2d_bytes_per_step': int(p_host.numel() * 8 + t_host.numel() * 4 + b_host.numel() * 8),
+                'd2h_bytes_per_step': int(x_host.numel() * 8), 'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': gpu_launches,
+        'clocks': clocks,
+    }
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        r = cpu_reference_pass(args.ref_level)
+        cpu_s = r['asm_s'] + r['condense_s'] + r['spmv_s'] + r['pcg_s']
+        line['cpu_baseline'] = {
+            'value': r['ndofs'] / cpu_s / 1e6, 'unit': 'MDOF/s', 'cores': 1, 'kind': 'port',
+            'sample': f"level {args.ref_level} ({r['ndofs']} DOFs) of the same mesh family, one pass: asm {r['asm_s']:.2f} s, "
+                      f"condense {r['condense_s']:.2f} s, SpMV {r['spmv_s'] * 1e3:.2f} ms, RS-AMG(sym. GS)-PCG "
+                      f"{r['pcg_s']:.2f} s / {r['iters']} its (AMG setup {r['amg_setup_s']:.2f} s separate)",
+            'assembly_mdof_s': r['ndofs'] / r['asm_s'] / 1e6,
+            'spmv_gbs': (12 * r['nnz'] + 20 * r['n']) / r['spmv_s'] / 1e9,
+            'pcg_ms_per_iter': r['pcg_s'] / max(r['iters'], 1) * 1e3,
+            'host_cores_available': os.cpu_count(), 'wall_s': time.perf_counter() - t0}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

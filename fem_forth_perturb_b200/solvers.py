@@ -260,49 +260,72 @@ def _flatten_dofs(S):
     raise NotImplementedError("Unable to flatten the given set of DOFs.")
 
 
+class CondensePlan:
+    """Reusable elimination of a fixed Dirichlet set from matrices sharing one sparsity pattern.
+
+    The count pass of ``condense`` (kept-row numbering, condensed indptr) depends only on the pattern and
+    on D, so an epsilon sweep or a re-assembly on the same mesh pays for it once."""
+
+    def __init__(self, A, I=None, D=None):
+        torch = L.require_cuda()
+        A = _to_device_csr(A)
+        n = A.shape[0]
+        if I is None and D is None:
+            raise Exception("Either I or D must be given!")
+        if I is not None and D is not None:
+            raise Exception("Give only I or only D!")
+        keep_h = np.zeros(n, dtype=np.int32)
+        if I is None:
+            keep_h[:] = 1
+            keep_h[D] = 0
+            I = np.nonzero(keep_h)[0]
+        else:
+            keep_h[I] = 1
+        self.I, self.n, self.pattern_key = I, n, A.pattern_key
+        dev = A.d_data.device
+        self.keep = torch.from_numpy(keep_h).to(dev)
+        self.newid = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        indptr_out = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        n_out, nnz_out = ctypes.c_int64(0), ctypes.c_int64(0)
+        L.check(L.lib().mwx_condense_count(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(self.keep),
+                                           L.ptr(self.newid), L.ptr(indptr_out), ctypes.byref(n_out),
+                                           ctypes.byref(nnz_out), L.stream()), 'mwx_condense_count')
+        self.n_out, self.nnz_out = int(n_out.value), int(nnz_out.value)
+        self.indptr_out = indptr_out[:self.n_out + 1].clone()
+        self.indices_out = torch.empty(self.nnz_out, dtype=torch.int32, device=dev)
+
+    def apply(self, A, b=None, x=None, values_out=None):
+        """-> (Aout DeviceCSR, bout or None); b/x may be numpy or device tensors."""
+        torch = L.require_cuda()
+        A = _to_device_csr(A)
+        if A.pattern_key != self.pattern_key:
+            raise ValueError("CondensePlan was built for a different sparsity pattern")
+        dev = A.d_data.device
+        vals = values_out if values_out is not None else torch.empty(self.nnz_out, dtype=torch.float64, device=dev)
+        have_b = b is not None
+        bd = _to_device_vec(b, dev) if have_b else None
+        xd = _to_device_vec(x, dev) if (have_b and x is not None) else None
+        b_out = torch.empty(self.n_out, dtype=torch.float64, device=dev) if have_b else None
+        L.check(L.lib().mwx_condense_fill(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data),
+                                          L.ptr(self.keep), L.ptr(self.newid), L.ptr(self.indptr_out),
+                                          L.ptr(self.indices_out), L.ptr(vals), L.ptr(bd), L.ptr(xd), L.ptr(b_out),
+                                          L.stream()), 'mwx_condense_fill')
+        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out))
+        return Aout, b_out
+
+
 def condense(A, b=None, x=None, I=None, D=None, expand=True):
     """ref utils.py:384-460 on the device: ``Aout = A[I].T[I].T``, ``bout = b[I] - A[I].T[D].T @ x[D]``.
     ``A`` may be a DeviceCSR (stays in HBM) or a scipy matrix (uploaded)."""
-    torch = L.require_cuda()
     D, I = _flatten_dofs(D), _flatten_dofs(I)
     A = _to_device_csr(A)
-    n = A.shape[0]
-    if x is None:
-        x = np.zeros(n)
-    if I is None and D is None:
-        raise Exception("Either I or D must be given!")
-    if I is not None and D is not None:
-        raise Exception("Give only I or only D!")
-    keep_h = np.zeros(n, dtype=np.int32)
-    if I is None:
-        keep_h[:] = 1
-        keep_h[D] = 0
-        I = np.nonzero(keep_h)[0]
-    else:
-        keep_h[I] = 1
-    dev = A.d_data.device
-    keep = torch.from_numpy(keep_h).to(dev)
-    newid = torch.empty(n + 1, dtype=torch.int32, device=dev)
-    indptr_out = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    n_out, nnz_out = ctypes.c_int64(0), ctypes.c_int64(0)
-    lib, st = L.lib(), L.stream()
-    L.check(lib.mwx_condense_count(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(keep), L.ptr(newid),
-                                   L.ptr(indptr_out), ctypes.byref(n_out), ctypes.byref(nnz_out), st),
-            'mwx_condense_count')
-    no, nz = int(n_out.value), int(nnz_out.value)
-    indices_out = torch.empty(nz, dtype=torch.int32, device=dev)
-    values_out = torch.empty(nz, dtype=torch.float64, device=dev)
-    have_b = b is not None
-    if have_b and not isinstance(b, (np.ndarray,)) and not hasattr(b, 'data_ptr'):
+    if b is not None and not isinstance(b, np.ndarray) and not hasattr(b, 'data_ptr'):
         raise NotImplementedError("condense: generalized eigenproblems (matrix b) are not on the device path")
-    bd = _to_device_vec(b, dev) if have_b else None
-    xd = _to_device_vec(x, dev) if have_b else None
-    b_out = torch.empty(no, dtype=torch.float64, device=dev) if have_b else None
-    L.check(lib.mwx_condense_fill(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(keep),
-                                  L.ptr(newid), L.ptr(indptr_out), L.ptr(indices_out), L.ptr(values_out),
-                                  L.ptr(bd), L.ptr(xd), L.ptr(b_out), st), 'mwx_condense_fill')
-    Aout = DeviceCSR(indptr_out[:no + 1].contiguous(), indices_out, values_out, (no, no))
-    ret = (Aout,) if not have_b else (Aout, b_out.cpu().numpy() if isinstance(b, np.ndarray) else b_out)
+    if x is None:
+        x = np.zeros(A.shape[0])
+    plan = CondensePlan(A, I=I, D=D)
+    Aout, b_out = plan.apply(A, b, x if b is not None else None)
+    ret = (Aout,) if b is None else (Aout, b_out.cpu().numpy() if isinstance(b, np.ndarray) else b_out)
     if expand:
-        ret += (x, I)
+        ret += (x, plan.I)
     return ret if len(ret) > 1 else ret[0]

@@ -216,8 +216,16 @@ def test_properties_at_4M_dofs(cuda):
     quad = interp(lambda x, y: x * x, lambda x, y: (2 * x, torch.zeros_like(x)))
     k1 = K.dot(one)
     assert float(k1.abs().max()) < 1e-9                       # constants are in the kernel
-    assert abs(float(torch.dot(lin, K.dot(lin))) - 1.0) < 1e-9                         # |grad x|^2 = 1
-    assert abs(float(torch.dot(quad, K.dot(quad))) - (4 * eps2 + 4.0 / 3.0)) < 1e-8   # 4 eps^2 + int 4x^2
+    # round-off budget of u.Ku: n * eps_mach * max|K| * max|u|^2 = 4.2e6 * 1.1e-16 * ~100 ~ 5e-8
+    assert abs(float(torch.dot(lin, K.dot(lin))) - 1.0) < 2e-7                         # |grad x|^2 = 1
+    assert abs(float(torch.dot(quad, K.dot(quad))) - (4 * eps2 + 4.0 / 3.0)) < 2e-7   # 4 eps^2 + int 4x^2
+    Kb = F.asm_gpu(F.b_load, basis)                            # max|K| ~ 4 -> budget ~ 2e-9
+    assert abs(float(torch.dot(lin, Kb.dot(lin))) - 1.0) < 1e-8
+    assert abs(float(torch.dot(quad, Kb.dot(quad))) - 4.0 / 3.0) < 1e-8
+    Ka = F.asm_gpu(F.a_load, basis)                            # hess(x^2) = diag(2, 0): |hess|^2 = 4
+    amax = float(Ka.d_data.abs().max())                        # ~ h^-2 = 4e6: budget n * eps_mach * max|A|
+    assert abs(float(torch.dot(quad, Ka.dot(quad))) - 4.0) < 1.1e-16 * K.shape[0] * amax
+    assert float(Ka.dot(lin).abs().max()) < 1e-13 * amax
     # symmetry: x.Ky == y.Kx
     g = torch.Generator(device=dev).manual_seed(7)
     x = torch.rand(K.shape[0], dtype=torch.float64, device=dev, generator=g)
@@ -241,10 +249,14 @@ def test_pcg_jacobi_matches_oracle_cg(cuda, level, eps):
     x, it = solver.solve_with_info(Kc, bc)
     assert solver.last['info'] == 0 and info_or == 0
     assert abs(it - it_or) <= 1                                  # +-1 iteration bar
-    # solution parity to 1e-10 needs both sides converged well below that
-    x_t, _ = F.solver_iter_krylov(Precondition=True, tol=1e-13).solve_with_info(Kc, bc)
+    # same algorithm, same stopping rule: the two iterates differ by round-off only
+    assert np.linalg.norm(x - x_or) <= 1e-9 * np.linalg.norm(x_or)
     x_d = pl.direct_solver(Kc, bc)
-    assert np.linalg.norm(x_t - x_d) <= 1e-10 * np.linalg.norm(x_d)
+    assert np.linalg.norm(x - x_d) <= 1e-5 * np.linalg.norm(x_d)          # tol 1e-8 times conditioning
+    if eps <= 1e-2:
+        # 1e-10 solution parity needs a system conditioned well enough to converge below it
+        x_t, _ = F.solver_iter_krylov(Precondition=True, tol=1e-12).solve_with_info(Kc, bc)
+        assert np.linalg.norm(x_t - x_d) <= 1e-10 * np.linalg.norm(x_d)
     # unpreconditioned flavour (Precondition omitted -> plain CG), as solver_iter_krylov allows
     x_p, it_p = F.solver_iter_krylov(tol=1e-8).solve_with_info(Kc, bc)
     _, _, it_po = cg141(Kc, bc, M=None, tol=1e-8)
