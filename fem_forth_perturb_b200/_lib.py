@@ -34,7 +34,10 @@ _SIGNATURES = {
     'mwx_axpby': [i64, f64, vp, f64, vp, vp, vp],
     'mwx_condense_count': [i64, vp, vp, vp, vp, vp, _pi64, _pi64, vp],
     'mwx_condense_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-    'mwx_spmv': [i64, vp, vp, vp, vp, vp, vp],
+    'mwx_hilbert_keys': [i64, vp, f64, f64, f64, vp, vp],
+    'mwx_csr_permute': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_gather_f64': [i64, vp, vp, vp, vp],
+    'mwx_spmv': [i64, i64, vp, vp, vp, vp, vp, vp],
     'mwx_csr_diagonal': [i64, vp, vp, vp, vp, vp],
     'mwx_pcg_jacobi': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp],
     'mwx_amg_setup_host': [i64, vp, vp, vp, f64, i32, i32, ctypes.POINTER(vp)],

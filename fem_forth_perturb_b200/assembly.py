@@ -17,10 +17,11 @@ from .forms import as_form
 class DeviceCSR:
     """CSR matrix resident in HBM (int64 indptr, int32 indices, fp64 data); scipy-compatible view."""
 
-    def __init__(self, indptr, indices, data, shape, pattern_key=None):
+    def __init__(self, indptr, indices, data, shape, pattern_key=None, coords=None):
         self.d_indptr, self.d_indices, self.d_data = indptr, indices, data
         self.shape = tuple(int(s) for s in shape)
         self.pattern_key = pattern_key if pattern_key is not None else (indptr.data_ptr(), indices.data_ptr())
+        self.coords = coords          # optional callable -> device (n, 2) DOF locations (locality key)
 
     # -- scipy-compatible surface ---------------------------------------------------------------
     @property
@@ -70,7 +71,7 @@ class DeviceCSR:
         b = other.d_data if other is not None else self.d_data
         L.check(L.lib().mwx_axpby(self.nnz, float(alpha), L.ptr(self.d_data), float(beta), L.ptr(b), L.ptr(out),
                                   L.stream()), 'mwx_axpby')
-        return DeviceCSR(self.d_indptr, self.d_indices, out, self.shape, self.pattern_key)
+        return DeviceCSR(self.d_indptr, self.d_indices, out, self.shape, self.pattern_key, self.coords)
 
     def __mul__(self, c):
         if np.isscalar(c):
@@ -106,7 +107,7 @@ class DeviceCSR:
         if xd.numel() != self.shape[1]:
             raise ValueError("dimension mismatch")
         y = torch.empty(self.shape[0], dtype=torch.float64, device=self.d_data.device)
-        L.check(L.lib().mwx_spmv(self.shape[0], L.ptr(self.d_indptr), L.ptr(self.d_indices), L.ptr(self.d_data),
+        L.check(L.lib().mwx_spmv(self.shape[0], self.nnz, L.ptr(self.d_indptr), L.ptr(self.d_indices), L.ptr(self.d_data),
                                  L.ptr(xd), L.ptr(y), L.stream()), 'mwx_spmv')
         return y.cpu().numpy() if is_np else y
 
@@ -152,7 +153,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
                                          L.ptr(pat['indices']), t.get('penalty_1', 0.0), t.get('penalty_2', 0.0),
                                          t.get('penalty_3', 0.0), float(sigma), L.ptr(vals), st),
                 'mwx_assemble_penalty')
-        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ib.N, ib.N))
+        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ib.N, ib.N), coords=ib.dof_coords)
     if not isinstance(ubasis, InteriorBasis):
         raise TypeError("asm_gpu expects an InteriorBasis or FacetBasis of this package")
     if f.kind != 'interior':
@@ -164,7 +165,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
                                     L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']), L.ptr(pat['indptr']),
                                     f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0), 0, L.ptr(vals), st),
             'mwx_assemble_morley')
-    return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N))
+    return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
 
 
 asm = asm_gpu

@@ -93,6 +93,20 @@ class InteriorBasis:
                                  nnz=int(nnz.value), max_row=int(maxrow.value))
         return self._pattern
 
+    def dof_coords(self):
+        """Device (N, 2) fp64 DOF locations (vertices, then facet midpoints): the locality key of the
+        fast-mode solver's internal renumbering."""
+        if getattr(self, '_coords', None) is None:
+            torch = L.require_cuda()
+            m = self.mesh
+            pxy = m.d_pxy.reshape(m.nv, 2)
+            if self.elem.facet_dofs:
+                f = m.d_facets.reshape(2, m.nf).long()
+                self._coords = torch.cat((pxy, 0.5 * (pxy[f[0]] + pxy[f[1]])), dim=0).contiguous()
+            else:
+                self._coords = pxy.contiguous()
+        return self._coords
+
     # -- boundary DOFs -----------------------------------------------------------------------------
     def find_dofs(self, facets=None):
         """``basis.find_dofs()`` -> {'all': DofsView of the boundary}; with a dict of facet sets,

@@ -226,7 +226,7 @@ static int estimate_rho(mwx_amg_dev *d, DLevel &L, cudaStream_t st) {
         if (it > 0) lam = nrm;                      // ||D^-1 A v_prev|| with ||v_prev|| = 1
         k_scale_by<<<vgrid(n), 256, 0, st>>>(n, v, nullptr, 1.0 / nrm, v);
         MWX_LAUNCH_CHECK();
-        rc = launch_spmv(n, L.A.ptr, L.A.idx, L.A.val, v, w, nullptr, nullptr, nullptr, nullptr, st);
+        rc = launch_spmv(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, v, w, nullptr, nullptr, nullptr, nullptr, st);
         if (rc) return rc;
         k_scale_by<<<vgrid(n), 256, 0, st>>>(n, w, L.dinv, 1.0, v);
         MWX_LAUNCH_CHECK();
@@ -356,7 +356,7 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
                 k_cheby_first_zero<<<vgrid(n), 256, 0, st>>>(n, b, L.dinv, omega, cur, L.d);
                 MWX_LAUNCH_CHECK();
             } else {
-                if ((rc = launch_smoother_step(n, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, 0.0, omega, st))) return rc;
+                if ((rc = launch_smoother_step(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, 0.0, omega, st))) return rc;
                 std::swap(cur, alt);
             }
         }
@@ -377,7 +377,7 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
                 k_cheby_first_zero<<<vgrid(n), 256, 0, st>>>(n, b, L.dinv, c2, cur, L.d);
                 MWX_LAUNCH_CHECK();
             } else {
-                if ((rc = launch_smoother_step(n, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, c1, c2, st))) return rc;
+                if ((rc = launch_smoother_step(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, c1, c2, st))) return rc;
                 std::swap(cur, alt);
             }
         }
@@ -393,10 +393,10 @@ static int cycle(mwx_amg_dev *d, int l, double *x, const double *b, cudaStream_t
     int rc;
     double *xs = x;
     if ((rc = smooth(d, L, x, b, true, &xs, st))) return rc;
-    if ((rc = launch_spmv_axpy(n, L.A.ptr, L.A.idx, L.A.val, xs, L.r, b, -1, st))) return rc;
+    if ((rc = launch_spmv_axpy(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, xs, L.r, b, -1, st))) return rc;
     DLevel &C = d->lv[(size_t)l + 1];
     const int64_t nc = C.A.rows;
-    if ((rc = launch_spmv(nc, L.R.ptr, L.R.idx, L.R.val, L.r, C.b, nullptr, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_spmv(nc, L.R.nnz, L.R.ptr, L.R.idx, L.R.val, L.r, C.b, nullptr, nullptr, nullptr, nullptr, st))) return rc;
     if (l + 1 == nl - 1) {
         k_dense_gemv<<<grid_for(nc * 32, 256), 256, 0, st>>>(nc, d->pinv, C.b, C.x);
         MWX_LAUNCH_CHECK();
@@ -404,7 +404,7 @@ static int cycle(mwx_amg_dev *d, int l, double *x, const double *b, cudaStream_t
         if ((rc = cycle(d, l + 1, C.x, C.b, st))) return rc;
     }
     // x += P x_c   (in place on whichever buffer holds the iterate)
-    if ((rc = launch_spmv_axpy(n, L.P.ptr, L.P.idx, L.P.val, C.x, xs, xs, +1, st))) return rc;
+    if ((rc = launch_spmv_axpy(n, L.P.nnz, L.P.ptr, L.P.idx, L.P.val, C.x, xs, xs, +1, st))) return rc;
     double *xo = xs;
     if (d->smoother == 0) {
         if ((rc = smooth(d, L, xs, b, false, &xo, st))) return rc;

@@ -19,8 +19,8 @@
 namespace mwx {
 namespace {
 
-constexpr int SPMV_ROWS = 128;
-constexpr int SPMV_CAP = SPMV_ROWS * 24;        // 24 KB of fp64 products per CTA
+constexpr int SPMV_ROWS = 128;                 // rows per tile
+constexpr int SPMV_THREADS = 256;              // all gather, the first SPMV_ROWS also own a row each
 constexpr int VEC_THREADS = 256;
 
 // Fold per-CTA partial sums: the last CTA to arrive adds them in index order.  Returns true in the
@@ -44,43 +44,160 @@ __device__ __forceinline__ bool fold_partials(double v_thread0, double *partials
     return true;
 }
 
+// ---- TMA bulk copy + mbarrier primitives (sm_90+/sm_100a PTX) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// Shared-memory plan of the SpMV CTA: two stages of (values, column indices) filled by TMA.
+constexpr int SPMV_STAGE_ELEMS = SPMV_ROWS * 20 + 8;                 // staged nonzeros per stage (<= 20 per row)
+constexpr int SPMV_STAGE_BYTES = SPMV_STAGE_ELEMS * 12;             // 8 B value + 4 B column
+constexpr int SPMV_SMEM_BYTES = 2 * SPMV_STAGE_BYTES + 64 + 32 * 8; // + barriers/meta + reduction scratch
+
 // MODE 0: y = A x   1: y = c - A x   2: y = c + A x      (c = `cvec`, may alias y for MODE 2)
 // MODE 3 (smoother step): d = c1 d + c2 dinv (c - A x);  y = x + d     (y must not alias x)
 struct SmootherArgs { const double *dinv; double *d; double c1, c2; };
+
+// Persistent CTAs stride over 128-row tiles.  One elected thread streams the tile's contiguous
+// values / column indices into shared memory with two TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx), one tile ahead of the consumers; the 128 threads then only issue the x gathers (all of
+// a thread's gathers are in flight together), write the products back in place, and one thread per
+// row adds its products in CSR order.
 template <bool DOT, int MODE>
-__global__ void __launch_bounds__(SPMV_ROWS) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
                                                     const int32_t *__restrict__ indices,
                                                     const double *__restrict__ values,
                                                     const double *__restrict__ x, double *y,
                                                     const double *cvec,
                                                     const double *__restrict__ dot_with,
                                                     double *__restrict__ dot_out, double *partials,
-                                                    unsigned int *ticket, SmootherArgs sm) {
-    __shared__ double prod[SPMV_CAP];
-    __shared__ double red[32];
-    const int64_t ntiles = (n + SPMV_ROWS - 1) / SPMV_ROWS;
-    double dacc = 0.0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = tile * SPMV_ROWS;
-        const int64_t r1 = r0 + SPMV_ROWS < n ? r0 + SPMV_ROWS : n;
-        const int64_t r = r0 + threadIdx.x;
-        const int64_t s0 = indptr[r0];
-        const int len = (int)min((int64_t)(SPMV_CAP + 1), indptr[r1] - s0);
-        int64_t a = 0, b = 0;
-        if (r < r1) { a = indptr[r]; b = indptr[r + 1]; }
-        double sum = 0.0;
-        if (len <= SPMV_CAP) {
-            const int32_t *ci = indices + s0;
-            const double *va = values + s0;
-#pragma unroll 4
-            for (int k = threadIdx.x; k < len; k += SPMV_ROWS) prod[k] = va[k] * __ldg(x + ci[k]);
-            __syncthreads();
-            for (int k = (int)(a - s0); k < (int)(b - s0); ++k) sum += prod[k];
-            __syncthreads();
+                                                    unsigned int *ticket, SmootherArgs sm, int tma_ok,
+                                                    int rows_per_tile) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    auto stage_vals = [&](int stage) { return reinterpret_cast<double *>(smem_raw + stage * SPMV_STAGE_BYTES); };
+    auto stage_cols = [&](int stage) {
+        return reinterpret_cast<int32_t *>(smem_raw + stage * SPMV_STAGE_BYTES + SPMV_STAGE_ELEMS * 8);
+    };
+    unsigned char *tail = smem_raw + 2 * SPMV_STAGE_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tail);                 // [2]
+    int64_t *s_base = reinterpret_cast<int64_t *>(tail + 16);           // [2] first staged nonzero
+    int32_t *s_nst = reinterpret_cast<int32_t *>(tail + 32);            // [2] staged count, -1 = direct path
+    double *red = reinterpret_cast<double *>(tail + 64);                // [32]
+
+    const int64_t ntiles = (n + rows_per_tile - 1) / rows_per_tile;
+    const int tid = threadIdx.x;
+    int64_t nnz_total = 0;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+        nnz_total = indptr[n];
+    }
+    // producer (thread 0): describe tile -> stage and start its TMA copies
+    auto tile_bounds = [&](int64_t tile, int64_t &s0, int64_t &s1) {
+        const int64_t r0 = tile * rows_per_tile;
+        const int64_t r1 = r0 + rows_per_tile < n ? r0 + rows_per_tile : n;
+        s0 = indptr[r0];
+        s1 = indptr[r1];
+    };
+    auto issue = [&](int64_t s0, int64_t s1, int stage) {
+        const int64_t base = s0 & ~(int64_t)3, end = (s1 + 3) & ~(int64_t)3;   // 16-byte aligned in both arrays
+        const int64_t nst = end - base;
+        if (tma_ok && nst <= SPMV_STAGE_ELEMS && end <= nnz_total && nst > 0) {
+            s_base[stage] = base;
+            s_nst[stage] = (int32_t)nst;
+            fence_proxy_async();                                   // consumers' generic accesses -> before the refill
+            mbar_expect_tx(&bar[stage], (uint32_t)(nst * 12));
+            bulk_g2s(stage_vals(stage), values + base, (uint32_t)(nst * 8), &bar[stage]);
+            bulk_g2s(stage_cols(stage), indices + base, (uint32_t)(nst * 4), &bar[stage]);
         } else {
-            for (int64_t k = a; k < b; ++k) sum += values[k] * __ldg(x + indices[k]);
+            s_base[stage] = s0;
+            s_nst[stage] = -1;
         }
-        if (r < r1) {
+    };
+    int64_t tile = blockIdx.x;
+    int64_t ns0 = 0, ns1 = 0;                 // thread 0: bounds of the NEXT tile, loaded one iteration early
+    if (tid == 0 && tile < ntiles) {
+        tile_bounds(tile, ns0, ns1);
+        issue(ns0, ns1, 0);
+        if (tile + gridDim.x < ntiles) tile_bounds(tile + gridDim.x, ns0, ns1);
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+    double dacc = 0.0;
+    for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+        const int stage = k & 1;
+        const int64_t next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles) {
+            issue(ns0, ns1, stage ^ 1);
+            if (next + gridDim.x < ntiles) tile_bounds(next + gridDim.x, ns0, ns1);   // lands during this tile
+        }
+        const int64_t r0 = tile * rows_per_tile;
+        const int64_t r1 = r0 + rows_per_tile < n ? r0 + rows_per_tile : n;
+        const int64_t r = r0 + tid;
+        const bool own_row = tid < rows_per_tile && r < r1;
+        int64_t a = 0, b = 0;
+        if (own_row) { a = indptr[r]; b = indptr[r + 1]; }
+        const int nst = s_nst[stage];
+        double sum = 0.0;
+        if (nst >= 0) {
+            const int64_t base = s_base[stage];
+            double *vs = stage_vals(stage);
+            const int32_t *cs = stage_cols(stage);
+            if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+            else            { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+            // all of this thread's gathers are issued before any is consumed (U x 2 in flight)
+            constexpr int U = (SPMV_STAGE_ELEMS + 2 * SPMV_THREADS - 1) / (2 * SPMV_THREADS);
+            int2 c[U];
+            double xa[U], xb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = tid * 2 + u * 2 * SPMV_THREADS;
+                c[u] = e < nst ? *reinterpret_cast<const int2 *>(cs + e) : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = tid * 2 + u * 2 * SPMV_THREADS;
+                if (e < nst) { xa[u] = __ldg(x + c[u].x); xb[u] = __ldg(x + c[u].y); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = tid * 2 + u * 2 * SPMV_THREADS;
+                if (e < nst) {
+                    double2 v = *reinterpret_cast<double2 *>(vs + e);
+                    v.x *= xa[u];
+                    v.y *= xb[u];
+                    *reinterpret_cast<double2 *>(vs + e) = v;
+                }
+            }
+            __syncthreads();
+            for (int e = (int)(a - base); e < (int)(b - base); ++e) sum += vs[e];
+        } else {
+            for (int64_t e = a; e < b; ++e) sum += values[e] * __ldg(x + indices[e]);
+        }
+        if (own_row) {
             if (MODE == 1) sum = cvec[r] - sum;
             if (MODE == 2) sum = cvec[r] + sum;
             if (MODE == 3) {
@@ -91,11 +208,12 @@ __global__ void __launch_bounds__(SPMV_ROWS) k_spmv(int64_t n, const int64_t *__
             y[r] = sum;
             if (DOT) dacc += dot_with[r] * sum;
         }
+        __syncthreads();                 // stage fully consumed before thread 0 refills it next iteration
     }
     if (DOT) {
         const double bs = block_sum(dacc, red);
         double total;
-        if (fold_partials(bs, partials, ticket, red, total) && threadIdx.x == 0) *dot_out = total;
+        if (fold_partials(bs, partials, ticket, red, total) && tid == 0) *dot_out = total;
     }
 }
 
@@ -207,9 +325,20 @@ inline unsigned vec_grid(int64_t n) {
     return (unsigned)(g < 1 ? 1 : g);
 }
 
-inline unsigned spmv_grid(int64_t n) {
-    int64_t g = (n + SPMV_ROWS - 1) / SPMV_ROWS;
-    const int64_t cap = (int64_t)sm_count() * 9;          // 9 CTAs x 24 KB smem per SM
+// Rows per tile such that an average tile (+25 %) fits one TMA stage; denser operators (AMG coarse
+// levels, restriction) get shorter tiles instead of falling off the staged path.
+inline int spmv_rows_per_tile(int64_t n, int64_t nnz) {
+    int rows = SPMV_ROWS;
+    if (nnz > 0 && n > 0) {
+        const double avg = (double)nnz / (double)n;
+        while (rows > 8 && rows * avg * 1.25 + 8 > SPMV_STAGE_ELEMS) rows >>= 1;
+    }
+    return rows;
+}
+
+inline unsigned spmv_grid(int64_t n, int ctas_per_sm, int rows_per_tile) {
+    int64_t g = (n + rows_per_tile - 1) / rows_per_tile;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;   // persistent: exactly one resident wave
     if (g > cap) g = cap;
     if (g > RED_MAX_BLOCKS) g = RED_MAX_BLOCKS;
     return (unsigned)(g < 1 ? 1 : g);
@@ -217,36 +346,51 @@ inline unsigned spmv_grid(int64_t n) {
 
 }  // namespace
 
-int launch_spmv(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+template <bool DOT, int MODE>
+int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
+                double *y, const double *c, const double *dot_with, double *dot_out, double *partials,
+                unsigned int *ticket, SmootherArgs sm, cudaStream_t st) {
+    static int ctas_per_sm = 0;                   // per instantiation; the attributes are per device function
+    if (!ctas_per_sm) {
+        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_BYTES));
+        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int occ = 0;
+        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<DOT, MODE>, SPMV_THREADS, SPMV_SMEM_BYTES));
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    // TMA bulk copies need 16-byte aligned global addresses; the kernel aligns offsets, the bases must be too
+    const int tma_ok = (((uintptr_t)values & 15) == 0 && ((uintptr_t)indices & 15) == 0) ? 1 : 0;
+    const int rows = spmv_rows_per_tile(n, nnz);
+    k_spmv<DOT, MODE><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SPMV_SMEM_BYTES, st>>>(
+        n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                 const double *x, double *y, const double *dot_with, double *dot_out, double *partials,
                 unsigned int *ticket, cudaStream_t st) {
-    const unsigned g = spmv_grid(n);
     if (dot_with)
-        k_spmv<true, 0><<<g, SPMV_ROWS, 0, st>>>(n, indptr, indices, values, x, y, nullptr, dot_with, dot_out, partials, ticket, SmootherArgs{});
-    else
-        k_spmv<false, 0><<<g, SPMV_ROWS, 0, st>>>(n, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, nullptr, SmootherArgs{});
-    MWX_LAUNCH_CHECK();
-    return 0;
+        return spmv_launch<true, 0>(n, nnz, indptr, indices, values, x, y, nullptr, dot_with, dot_out, partials, ticket,
+                                    SmootherArgs{}, st);
+    return spmv_launch<false, 0>(n, nnz, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 SmootherArgs{}, st);
 }
 
-int launch_spmv_axpy(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+int launch_spmv_axpy(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                      const double *x, double *y, const double *c, int sign, cudaStream_t st) {
-    const unsigned g = spmv_grid(n);
     if (sign < 0)
-        k_spmv<false, 1><<<g, SPMV_ROWS, 0, st>>>(n, indptr, indices, values, x, y, c, nullptr, nullptr, nullptr, nullptr, SmootherArgs{});
-    else
-        k_spmv<false, 2><<<g, SPMV_ROWS, 0, st>>>(n, indptr, indices, values, x, y, c, nullptr, nullptr, nullptr, nullptr, SmootherArgs{});
-    MWX_LAUNCH_CHECK();
-    return 0;
+        return spmv_launch<false, 1>(n, nnz, indptr, indices, values, x, y, c, nullptr, nullptr, nullptr, nullptr,
+                                     SmootherArgs{}, st);
+    return spmv_launch<false, 2>(n, nnz, indptr, indices, values, x, y, c, nullptr, nullptr, nullptr, nullptr,
+                                 SmootherArgs{}, st);
 }
 
-int launch_smoother_step(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+int launch_smoother_step(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                          const double *x_in, double *x_out, const double *b, const double *dinv, double *d,
                          double c1, double c2, cudaStream_t st) {
-    k_spmv<false, 3><<<spmv_grid(n), SPMV_ROWS, 0, st>>>(n, indptr, indices, values, x_in, x_out, b, nullptr,
-                                                         nullptr, nullptr, nullptr, SmootherArgs{dinv, d, c1, c2});
-    MWX_LAUNCH_CHECK();
-    return 0;
+    return spmv_launch<false, 3>(n, nnz, indptr, indices, values, x_in, x_out, b, nullptr, nullptr, nullptr, nullptr,
+                                 SmootherArgs{dinv, d, c1, c2}, st);
 }
 
 int launch_residual(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
@@ -288,6 +432,8 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
     MWX_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
     if (maxiter <= 0) maxiter = 10 * n;
     double h[2];
+    int64_t nnz = -1;
+    MWX_CUDA(cudaMemcpyAsync(&nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     // ||b|| and r = b - A*0 = b
     int rc = launch_dot(n, b, b, &sc.p->aux, partials.p, &sc.p->ticket[0], st);
     if (rc) return rc;
@@ -313,7 +459,7 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
         }
         k_p_update<<<vec_grid(n), VEC_THREADS, 0, st>>>(n, r, dinv, jacobi ? nullptr : z, p, sc.p, it == 1);
         MWX_LAUNCH_CHECK();
-        rc = launch_spmv(n, indptr, indices, values, p, q, p, &sc.p->pq, partials.p, &sc.p->ticket[0], st);
+        rc = launch_spmv(n, nnz, indptr, indices, values, p, q, p, &sc.p->pq, partials.p, &sc.p->ticket[0], st);
         if (rc) return rc;
         k_xr_update<<<vec_grid(n), VEC_THREADS, 0, st>>>(n, p, q, x, r, dinv, sc.p, partials.p, jacobi ? 1 : 0);
         MWX_LAUNCH_CHECK();
@@ -345,10 +491,10 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
 
 using namespace mwx;
 
-extern "C" int mwx_spmv(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
-                        const double *x, double *y, void *stream) {
+extern "C" int mwx_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                        const double *values, const double *x, double *y, void *stream) {
     if (n <= 0 || !indptr || !indices || !values || !x || !y) return MWX_E_BADARG;
-    return launch_spmv(n, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
+    return launch_spmv(n, nnz, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
 }
 
 extern "C" int mwx_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices,

@@ -16,19 +16,20 @@ struct CgScalars {
 
 constexpr int RED_MAX_BLOCKS = 4096;   // partial-sum slots per reduction site
 
+// `nnz` in the SpMV launchers is a hint (-1 = unknown) used to size the row tiles.
 // y = A x (CSR, int64 indptr, int32 cols, fp64).  If dot_with != nullptr also accumulates
 // sum_i dot_with[i] * y[i] into *dot_out deterministically (per-CTA partials, last CTA folds them in
 // index order).  partials: RED_MAX_BLOCKS doubles, ticket: zero-initialised counter.
-int launch_spmv(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+int launch_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                 const double *x, double *y, const double *dot_with, double *dot_out, double *partials,
                 unsigned int *ticket, cudaStream_t st);
 
 // y = c - A x (sign < 0) or y = c + A x (sign > 0); c may alias y.
-int launch_spmv_axpy(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+int launch_spmv_axpy(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                      const double *x, double *y, const double *c, int sign, cudaStream_t st);
 
 // One polynomial-smoother step: d = c1 d + c2 dinv (b - A x_in);  x_out = x_in + d  (x_out != x_in).
-int launch_smoother_step(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+int launch_smoother_step(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                          const double *x_in, double *x_out, const double *b, const double *dinv, double *d,
                          double c1, double c2, cudaStream_t st);
 

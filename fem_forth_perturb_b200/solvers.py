@@ -33,6 +33,58 @@ def _to_device_vec(b, device):
     return b.to(device=device, dtype=torch.float64).contiguous()
 
 
+class Reordering:
+    """Hilbert-curve renumbering of a system (internal to the throughput solvers; results are permuted back).
+
+    perm[i] = old index of new DOF i.  Built from the DOF locations that ``asm_gpu`` attaches to its
+    matrices; a matrix without locations (e.g. uploaded from scipy) cannot be reordered and is solved as is."""
+
+    def __init__(self, coords):
+        torch = L.require_cuda()
+        xy = coords.contiguous()
+        n = xy.shape[0]
+        lo, hi = xy.min(dim=0).values, xy.max(dim=0).values
+        extent = float((hi - lo).max().item()) or 1.0
+        keys = torch.empty(n, dtype=torch.int64, device=xy.device)
+        L.check(L.lib().mwx_hilbert_keys(n, L.ptr(xy), float(lo[0].item()), float(lo[1].item()), extent, L.ptr(keys),
+                                         L.stream()), 'mwx_hilbert_keys')
+        order = torch.sort(keys, stable=True).indices               # library sort: setup only
+        self.perm = order.to(torch.int32)
+        self.iperm = torch.empty(n, dtype=torch.int32, device=xy.device)
+        self.iperm[order] = torch.arange(n, dtype=torch.int32, device=xy.device)
+        self.n = n
+
+    @classmethod
+    def for_matrix(cls, A):
+        if getattr(A, 'coords', None) is None:
+            return None
+        return cls(A.coords())
+
+    def matrix(self, A, out=None):
+        torch = L.require_cuda()
+        dev = A.d_data.device
+        if out is None:
+            out = (torch.empty(self.n + 1, dtype=torch.int64, device=dev),
+                   torch.empty(A.nnz, dtype=torch.int32, device=dev),
+                   torch.empty(A.nnz, dtype=torch.float64, device=dev))
+        L.check(L.lib().mwx_csr_permute(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data),
+                                        L.ptr(self.perm), L.ptr(self.iperm), L.ptr(out[0]), L.ptr(out[1]),
+                                        L.ptr(out[2]), L.stream()), 'mwx_csr_permute')
+        return DeviceCSR(out[0], out[1], out[2], A.shape)
+
+    def _gather(self, v, idx):
+        torch = L.require_cuda()
+        out = torch.empty_like(v)
+        L.check(L.lib().mwx_gather_f64(self.n, L.ptr(v), L.ptr(idx), L.ptr(out), L.stream()), 'mwx_gather_f64')
+        return out
+
+    def forward(self, v):          # old numbering -> new
+        return self._gather(v, self.perm)
+
+    def backward(self, v):         # new numbering -> old
+        return self._gather(v, self.iperm)
+
+
 class AMGHierarchy:
     """``pyamg.ruge_stuben_solver(A)`` (host C++ setup, timed) uploaded once to the device.
 
@@ -41,13 +93,24 @@ class AMGHierarchy:
     """
     MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2}
 
-    def __init__(self, A, mode='parity', degree=3, theta=0.25, max_levels=10, max_coarse=10):
+    def __init__(self, A, mode='parity', degree=3, theta=0.25, max_levels=10, max_coarse=10, reorder=None):
         torch = L.require_cuda()
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {list(self.MODES)}")
         lib = L.lib()
         A = _to_device_csr(A)
         self.n, self.mode = A.shape[0], mode
+        # fast modes run on a locality-renumbered copy; parity mode must keep skfem's order (GS depends on it)
+        if reorder is None:
+            reorder = mode != 'parity'
+        if reorder and mode == 'parity':
+            raise ValueError("parity mode reproduces lexicographic Gauss-Seidel in skfem's numbering; reorder=False")
+        t0 = time.perf_counter()
+        self.reordering = Reordering.for_matrix(A) if reorder else None
+        if self.reordering is not None:
+            A = self.reordering.matrix(A)
+            torch.cuda.synchronize()
+        self.reorder_seconds = time.perf_counter() - t0
         t0 = time.perf_counter()
         ip = np.ascontiguousarray(A.d_indptr.cpu().numpy(), dtype=np.int64)
         ix = np.ascontiguousarray(A.d_indices.cpu().numpy(), dtype=np.int32)
@@ -115,13 +178,17 @@ class AMGHierarchy:
             pass
 
 
-def _run_pcg(A, b, tol, maxiter, precondition=True, amg=None):
+def _run_pcg(A, b, tol, maxiter, precondition=True, amg=None, reordering=None):
     """Device PCG; returns (x torch, iters, info, resid)."""
     torch = L.require_cuda()
     A = _to_device_csr(A)
     n = A.shape[0]
     dev = A.d_data.device
     bd = _to_device_vec(b, dev)
+    ro = reordering if reordering is not None else (amg.reordering if amg is not None else None)
+    if ro is not None:
+        A = ro.matrix(A)
+        bd = ro.forward(bd)
     x = torch.empty(n, dtype=torch.float64, device=dev)
     work = torch.empty(4 * n, dtype=torch.float64, device=dev)
     iters, info, resid = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_double(0.0)
@@ -136,6 +203,8 @@ def _run_pcg(A, b, tol, maxiter, precondition=True, amg=None):
                                  ctypes.byref(resid), L.stream())
     if rc not in (0, -3):                       # -3 = MWX_E_NOCONV (breakdown): reported through info
         L.check(rc, 'mwx_pcg')
+    if ro is not None:
+        x = ro.backward(x)
     return x, int(iters.value), int(info.value), float(resid.value)
 
 
@@ -167,9 +236,12 @@ def _make_krylov(print_iters, krylov=None, verbose=False, **kwargs):
         kwargs.update(solve_time_kwargs)
         kw = dict(kwargs)
         pre = bool(kw.pop('Precondition', False)) is True
+        reorder = bool(kw.pop('reorder', False))
         _reject_host_callables(kw)
         t0 = time.perf_counter()
-        x, it, info, resid = _run_pcg(A, b, kw.get('tol', 1e-5), kw.get('maxiter'), precondition=pre)
+        A = _to_device_csr(A)
+        ro = Reordering.for_matrix(A) if reorder else None
+        x, it, info, resid = _run_pcg(A, b, kw.get('tol', 1e-5), kw.get('maxiter'), precondition=pre, reordering=ro)
         solver.last = dict(iters=it, info=info, resid=resid, solve_seconds=time.perf_counter() - t0)
         if print_iters:
             print('cg', 'total interation steps:', it)
@@ -282,6 +354,7 @@ class CondensePlan:
         else:
             keep_h[I] = 1
         self.I, self.n, self.pattern_key = I, n, A.pattern_key
+        self._I_dev = None
         dev = A.d_data.device
         self.keep = torch.from_numpy(keep_h).to(dev)
         self.newid = torch.empty(n + 1, dtype=torch.int32, device=dev)
@@ -310,7 +383,15 @@ class CondensePlan:
                                           L.ptr(self.keep), L.ptr(self.newid), L.ptr(self.indptr_out),
                                           L.ptr(self.indices_out), L.ptr(vals), L.ptr(bd), L.ptr(xd), L.ptr(b_out),
                                           L.stream()), 'mwx_condense_fill')
-        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out))
+        coords = None
+        if getattr(A, 'coords', None) is not None:
+            src, plan = A.coords, self
+
+            def coords():
+                if plan._I_dev is None:
+                    plan._I_dev = torch.from_numpy(np.ascontiguousarray(plan.I, dtype=np.int64)).to(dev)
+                return src()[plan._I_dev]
+        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out), coords=coords)
         return Aout, b_out
 
 

@@ -120,10 +120,23 @@ int mwx_condense_fill(int64_t n, const int64_t *indptr, const int32_t *indices,
                       const int64_t *indptr_out, int32_t *indices_out, double *values_out,
                       const double *b, const double *x, double *b_out, void *stream);
 
+/* ------------------------------------------------------------------ locality renumbering (internal to the fast solver)
+ * No reference counterpart.  keys[i] = position of DOF location xy[i] (interleaved x,y) along a Hilbert
+ * curve over the square [x0, x0+extent] x [y0, y0+extent]; sorting the keys gives the permutation. */
+int mwx_hilbert_keys(int64_t n, const double *xy, double x0, double y0, double extent, int64_t *keys,
+                     void *stream);
+/* B = P A P^T: row i of B is row perm[i] of A, columns renumbered through iperm and re-sorted.
+ * indptr_out (n+1), indices_out / values_out (nnz). */
+int mwx_csr_permute(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                    const int32_t *perm, const int32_t *iperm, int64_t *indptr_out, int32_t *indices_out,
+                    double *values_out, void *stream);
+/* dst[i] = src[idx[i]]  (b -> P b, x -> P^T x). */
+int mwx_gather_f64(int64_t n, const double *src, const int32_t *idx, double *dst, void *stream);
+
 /* ------------------------------------------------------------------ SpMV / vector kernels (hot path B)
  * y = A x.  Replaces scipy csr_matvec inside spl.cg  ref main/example1/utils.py:157. */
-int mwx_spmv(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
-             const double *x, double *y, void *stream);
+int mwx_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+             const double *values, const double *x, double *y, void *stream);   /* nnz: tiling hint, -1 = unknown */
 /* diag[i] = A[i,i] (0 if absent): build_pc_diag, ref main/example1/utils.py:48-50. */
 int mwx_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices,
                      const double *values, double *diag, void *stream);

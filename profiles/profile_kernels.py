@@ -22,12 +22,15 @@ bf = gm.boundary_facets()
 D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
 plan = F.CondensePlan(K2, D=D)
 Kc, _ = plan.apply(K2)
+if os.environ.get('MWX_PROFILE_REORDER', '1') == '1':
+    from fem_forth_perturb_b200.solvers import Reordering
+    Kc = Reordering.for_matrix(Kc).matrix(Kc)          # the numbering the fast-mode solver runs on
 n = Kc.shape[0]
 x = torch.rand(n, dtype=torch.float64, device='cuda')
 y = torch.empty_like(x)
 for _ in range(3):
     K2 = F.asm_gpu(form, basis, out=K2.d_data)
-    L.check(L.lib().mwx_spmv(n, L.ptr(Kc.d_indptr), L.ptr(Kc.d_indices), L.ptr(Kc.d_data), L.ptr(x), L.ptr(y), L.stream()))
+    L.check(L.lib().mwx_spmv(n, Kc.nnz, L.ptr(Kc.d_indptr), L.ptr(Kc.d_indices), L.ptr(Kc.d_data), L.ptr(x), L.ptr(y), L.stream()))
 torch.cuda.synchronize()
 if maxit:
     b = Kc.dot(x)

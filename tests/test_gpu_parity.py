@@ -260,7 +260,7 @@ def test_pcg_jacobi_matches_oracle_cg(cuda, level, eps):
     # unpreconditioned flavour (Precondition omitted -> plain CG), as solver_iter_krylov allows
     x_p, it_p = F.solver_iter_krylov(tol=1e-8).solve_with_info(Kc, bc)
     _, _, it_po = cg141(Kc, bc, M=None, tol=1e-8)
-    assert abs(it_p - it_po) <= max(1, it_po // 100)
+    assert abs(it_p - it_po) <= max(1, it_po // 20)        # hundreds of its: round-off sensitive
 
 
 def test_pcg_edge_cases(cuda):
@@ -325,6 +325,43 @@ def test_amg_fast_modes_converge_to_the_same_solution(cuda, mode):
     assert solver.last['info'] == 0 and it < 80
     x_d = pl.direct_solver(Kc, bc)
     assert np.linalg.norm(x - x_d) <= 1e-10 * np.linalg.norm(x_d)
+
+
+def test_locality_reordering_is_a_similarity_transform(cuda):
+    """Fast-mode solvers run on P A P^T (Hilbert order of the DOF locations) and permute back."""
+    import fem_forth_perturb_b200 as F
+    from fem_forth_perturb_b200.solvers import Reordering
+    gm = F.MeshTri().refine(5)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    K = F.asm_gpu(1e-4 * F.a_load + F.b_load, basis)
+    bf = gm.boundary_facets()
+    D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal(K.shape[0])
+    Kc, bc, _, I = F.condense(K, f, D=D)
+    assert Kc.coords is not None
+    ro = Reordering.for_matrix(Kc)
+    perm = ro.perm.cpu().numpy()
+    assert sorted(perm.tolist()) == list(range(Kc.shape[0]))
+    assert np.array_equal(ro.iperm.cpu().numpy()[perm], np.arange(Kc.shape[0]))
+    Ks = Kc.tocsr()
+    Kp = ro.matrix(Kc).tocsr()
+    ref = Ks[perm][:, perm].tocsr(); ref.sort_indices()
+    assert np.array_equal(Kp.indptr, ref.indptr) and np.array_equal(Kp.indices, ref.indices)
+    assert np.array_equal(Kp.data, ref.data)                      # pure data movement: bit-exact
+    # locality: consecutive DOFs along the curve are geometric neighbours (mean jump ~ h, not ~ 1)
+    xy = Kc.coords().cpu().numpy()[perm]
+    jump = np.linalg.norm(np.diff(xy, axis=0), axis=1)
+    assert np.median(jump) < 4 * 2.0 ** -5 and jump.mean() < np.linalg.norm(np.diff(Kc.coords().cpu().numpy(), axis=0), axis=1).mean()
+    # solves agree with the un-reordered ones
+    x_d = pl.direct_solver(Ks, bc)
+    for solver in (F.solver_iter_mgcg(tol=1e-12, mode='chebyshev'), F.solver_iter_mgcg(tol=1e-12, mode='jacobi'),
+                   F.solver_iter_krylov(Precondition=True, tol=1e-12, reorder=True)):
+        x, it = solver.solve_with_info(Kc, bc)
+        assert solver.last['info'] == 0
+        assert np.linalg.norm(x - x_d) <= 1e-10 * np.linalg.norm(x_d)
+    with pytest.raises(ValueError):
+        F.AMGHierarchy(Kc, mode='parity', reorder=True)
 
 
 def test_mgcg_iter_prints_like_the_reference(cuda, capsys):

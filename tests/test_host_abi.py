@@ -135,7 +135,7 @@ def test_amg_setup_tiny_and_bad_arguments():
     assert len(nat) == 1 and nat[0][0][1] is None
     h = ctypes.c_void_p()
     assert lib.mwx_amg_setup_host(0, None, None, None, 0.25, 10, 10, ctypes.byref(h)) == -1
-    assert lib.mwx_spmv(0, None, None, None, None, None, None) == -1
+    assert lib.mwx_spmv(0, -1, None, None, None, None, None, None) == -1
     assert lib.mwx_pcg_jacobi(4, None, None, None, None, None, 1e-8, 0, 1, None, None, None, None, None) == -1
 
 
