@@ -38,6 +38,7 @@ _SIGNATURES = {
     'mwx_csr_permute': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_gather_f64': [i64, vp, vp, vp, vp],
     'mwx_spmv': [i64, i64, vp, vp, vp, vp, vp, vp],
+    'mwx_spmv_plan': [i64, vp, _pi32, vp],
     'mwx_csr_diagonal': [i64, vp, vp, vp, vp, vp],
     'mwx_pcg_jacobi': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp],
     'mwx_amg_setup_host': [i64, vp, vp, vp, f64, i32, i32, ctypes.POINTER(vp)],
@@ -50,6 +51,7 @@ _SIGNATURES = {
     'mwx_gs_wavefronts_backward_host': [i64, vp, vp, vp, vp, _pi64],
     'mwx_amg_upload': [vp, i32, i32, vp, ctypes.POINTER(vp), vp],
     'mwx_amg_level_rho': [vp, i32, _pf64],
+    'mwx_amg_set_chebyshev': [vp, i32, f64],
     'mwx_amg_destroy_dev': [vp],
     'mwx_amg_vcycle': [vp, vp, vp, vp],
     'mwx_pcg_amg': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp],

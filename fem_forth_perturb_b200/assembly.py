@@ -22,6 +22,16 @@ class DeviceCSR:
         self.shape = tuple(int(s) for s in shape)
         self.pattern_key = pattern_key if pattern_key is not None else (indptr.data_ptr(), indices.data_ptr())
         self.coords = coords          # optional callable -> device (n, 2) DOF locations (locality key)
+        self._spmv_plan = None
+
+    def spmv_hint(self):
+        """-(tile rows) planned once per matrix for mwx_spmv (exact fit of the TMA stage)."""
+        if self._spmv_plan is None:
+            rows = ctypes.c_int32(0)
+            L.check(L.lib().mwx_spmv_plan(self.shape[0], L.ptr(self.d_indptr), ctypes.byref(rows), L.stream()),
+                    'mwx_spmv_plan')
+            self._spmv_plan = -int(rows.value)
+        return self._spmv_plan
 
     # -- scipy-compatible surface ---------------------------------------------------------------
     @property
@@ -107,7 +117,7 @@ class DeviceCSR:
         if xd.numel() != self.shape[1]:
             raise ValueError("dimension mismatch")
         y = torch.empty(self.shape[0], dtype=torch.float64, device=self.d_data.device)
-        L.check(L.lib().mwx_spmv(self.shape[0], self.nnz, L.ptr(self.d_indptr), L.ptr(self.d_indices), L.ptr(self.d_data),
+        L.check(L.lib().mwx_spmv(self.shape[0], self.spmv_hint(), L.ptr(self.d_indptr), L.ptr(self.d_indices), L.ptr(self.d_data),
                                  L.ptr(xd), L.ptr(y), L.stream()), 'mwx_spmv')
         return y.cpu().numpy() if is_np else y
 

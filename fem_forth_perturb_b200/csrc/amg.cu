@@ -26,6 +26,7 @@ namespace {
 
 struct DCsr {
     int64_t rows = 0, cols = 0, nnz = 0;
+    int64_t plan = -1;                         // -(planned SpMV tile height), see spmv_plan_rows
     int64_t *ptr = nullptr;
     int32_t *idx = nullptr;
     double *val = nullptr;
@@ -120,6 +121,9 @@ int upload_csr(const mwx_amg_host_t *h, int level, int which, DCsr &out, cudaStr
     if ((rc = upload(idx, &out.idx, st))) return rc;
     if ((rc = upload(val, &out.val, st))) return rc;
     MWX_CUDA(cudaStreamSynchronize(st));       // host staging vectors go out of scope
+    int tile_rows = 0;
+    if ((rc = spmv_plan_rows(out.rows, out.ptr, &tile_rows, st))) return rc;
+    out.plan = -(int64_t)tile_rows;
     return 0;
 }
 
@@ -189,8 +193,8 @@ struct mwx_amg_dev {
     std::vector<DLevel> lv;
     double *pinv = nullptr;              // dense (n_last x n_last), row-major
     int64_t n_last = 0;
-    int smoother = 0, degree = 3;
-    double cheb_ratio = 30.0;
+    int smoother = 0, degree = 2;
+    double cheb_ratio = 10.0;
     CgScalars *sc = nullptr;
     double *partials = nullptr;
 };
@@ -226,7 +230,7 @@ static int estimate_rho(mwx_amg_dev *d, DLevel &L, cudaStream_t st) {
         if (it > 0) lam = nrm;                      // ||D^-1 A v_prev|| with ||v_prev|| = 1
         k_scale_by<<<vgrid(n), 256, 0, st>>>(n, v, nullptr, 1.0 / nrm, v);
         MWX_LAUNCH_CHECK();
-        rc = launch_spmv(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, v, w, nullptr, nullptr, nullptr, nullptr, st);
+        rc = launch_spmv(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, v, w, nullptr, nullptr, nullptr, nullptr, st);
         if (rc) return rc;
         k_scale_by<<<vgrid(n), 256, 0, st>>>(n, w, L.dinv, 1.0, v);
         MWX_LAUNCH_CHECK();
@@ -249,7 +253,7 @@ extern "C" int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t
     auto *d = new (std::nothrow) mwx_amg_dev();
     if (!d) return MWX_E_NOMEM;
     d->smoother = smoother;
-    d->degree = cheby_degree > 0 ? cheby_degree : 3;
+    d->degree = cheby_degree > 0 ? cheby_degree : 2;
     d->lv.resize((size_t)nl);
     int rc = 0;
     auto fail = [&](int code) { mwx_amg_destroy_dev(d); return code; };
@@ -356,7 +360,7 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
                 k_cheby_first_zero<<<vgrid(n), 256, 0, st>>>(n, b, L.dinv, omega, cur, L.d);
                 MWX_LAUNCH_CHECK();
             } else {
-                if ((rc = launch_smoother_step(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, 0.0, omega, st))) return rc;
+                if ((rc = launch_smoother_step(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, 0.0, omega, st))) return rc;
                 std::swap(cur, alt);
             }
         }
@@ -377,7 +381,7 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
                 k_cheby_first_zero<<<vgrid(n), 256, 0, st>>>(n, b, L.dinv, c2, cur, L.d);
                 MWX_LAUNCH_CHECK();
             } else {
-                if ((rc = launch_smoother_step(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, c1, c2, st))) return rc;
+                if ((rc = launch_smoother_step(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, c1, c2, st))) return rc;
                 std::swap(cur, alt);
             }
         }
@@ -393,10 +397,10 @@ static int cycle(mwx_amg_dev *d, int l, double *x, const double *b, cudaStream_t
     int rc;
     double *xs = x;
     if ((rc = smooth(d, L, x, b, true, &xs, st))) return rc;
-    if ((rc = launch_spmv_axpy(n, L.A.nnz, L.A.ptr, L.A.idx, L.A.val, xs, L.r, b, -1, st))) return rc;
+    if ((rc = launch_spmv_axpy(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, xs, L.r, b, -1, st))) return rc;
     DLevel &C = d->lv[(size_t)l + 1];
     const int64_t nc = C.A.rows;
-    if ((rc = launch_spmv(nc, L.R.nnz, L.R.ptr, L.R.idx, L.R.val, L.r, C.b, nullptr, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_spmv(nc, L.R.plan, L.R.ptr, L.R.idx, L.R.val, L.r, C.b, nullptr, nullptr, nullptr, nullptr, st))) return rc;
     if (l + 1 == nl - 1) {
         k_dense_gemv<<<grid_for(nc * 32, 256), 256, 0, st>>>(nc, d->pinv, C.b, C.x);
         MWX_LAUNCH_CHECK();
@@ -404,7 +408,7 @@ static int cycle(mwx_amg_dev *d, int l, double *x, const double *b, cudaStream_t
         if ((rc = cycle(d, l + 1, C.x, C.b, st))) return rc;
     }
     // x += P x_c   (in place on whichever buffer holds the iterate)
-    if ((rc = launch_spmv_axpy(n, L.P.nnz, L.P.ptr, L.P.idx, L.P.val, C.x, xs, xs, +1, st))) return rc;
+    if ((rc = launch_spmv_axpy(n, L.P.plan, L.P.ptr, L.P.idx, L.P.val, C.x, xs, xs, +1, st))) return rc;
     double *xo = xs;
     if (d->smoother == 0) {
         if ((rc = smooth(d, L, xs, b, false, &xo, st))) return rc;
@@ -447,6 +451,13 @@ extern "C" int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, c
     double *r = work, *z = work + n, *p = work + 2 * n, *q = work + 3 * n;
     return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, nullptr, amg_precond, d, r, z, p, q,
                     iters_host, info_host, resid_host, as_stream(stream));
+}
+
+extern "C" int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ratio) {
+    if (!d || degree < 1 || degree > 16 || !(ratio > 1.0)) return MWX_E_BADARG;
+    d->degree = degree;
+    d->cheb_ratio = ratio;
+    return 0;
 }
 
 extern "C" int mwx_amg_level_rho(const mwx_amg_dev_t *d, int32_t level, double *rho_host) {

@@ -20,7 +20,8 @@ namespace mwx {
 namespace {
 
 constexpr int SPMV_ROWS = 128;                 // rows per tile
-constexpr int SPMV_THREADS = 256;              // all gather, the first SPMV_ROWS also own a row each
+constexpr int SPMV_THREADS = 256;              // all threads gather; rows of a tile are dealt round-robin
+constexpr int SPMV_MAX_TILE_ROWS = 1024;       // very sparse operators (prolongation): long tiles
 constexpr int VEC_THREADS = 256;
 
 // Fold per-CTA partial sums: the last CTA to arrive adds them in index order.  Returns true in the
@@ -86,7 +87,7 @@ struct SmootherArgs { const double *dinv; double *d; double c1, c2; };
 // a thread's gathers are in flight together), write the products back in place, and one thread per
 // row adds its products in CSR order.
 template <bool DOT, int MODE>
-__global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
                                                     const int32_t *__restrict__ indices,
                                                     const double *__restrict__ values,
                                                     const double *__restrict__ x, double *y,
@@ -156,15 +157,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, const int64_t 
         }
         const int64_t r0 = tile * rows_per_tile;
         const int64_t r1 = r0 + rows_per_tile < n ? r0 + rows_per_tile : n;
-        const int64_t r = r0 + tid;
-        const bool own_row = tid < rows_per_tile && r < r1;
-        int64_t a = 0, b = 0;
-        if (own_row) { a = indptr[r]; b = indptr[r + 1]; }
         const int nst = s_nst[stage];
-        double sum = 0.0;
+        const int64_t base = s_base[stage];
+        double *vs = stage_vals(stage);
         if (nst >= 0) {
-            const int64_t base = s_base[stage];
-            double *vs = stage_vals(stage);
             const int32_t *cs = stage_cols(stage);
             if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
             else            { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
@@ -193,11 +189,16 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, const int64_t 
                 }
             }
             __syncthreads();
-            for (int e = (int)(a - base); e < (int)(b - base); ++e) sum += vs[e];
-        } else {
-            for (int64_t e = a; e < b; ++e) sum += values[e] * __ldg(x + indices[e]);
         }
-        if (own_row) {
+        // one thread per row (a thread owns several rows when the tile is longer than the CTA)
+        for (int64_t r = r0 + tid; r < r1; r += SPMV_THREADS) {
+            const int64_t a = indptr[r], b = indptr[r + 1];
+            double sum = 0.0;
+            if (nst >= 0) {
+                for (int e = (int)(a - base); e < (int)(b - base); ++e) sum += vs[e];
+            } else {
+                for (int64_t e = a; e < b; ++e) sum += values[e] * __ldg(x + indices[e]);
+            }
             if (MODE == 1) sum = cvec[r] - sum;
             if (MODE == 2) sum = cvec[r] + sum;
             if (MODE == 3) {
@@ -331,9 +332,33 @@ inline int spmv_rows_per_tile(int64_t n, int64_t nnz) {
     int rows = SPMV_ROWS;
     if (nnz > 0 && n > 0) {
         const double avg = (double)nnz / (double)n;
-        while (rows > 8 && rows * avg * 1.25 + 8 > SPMV_STAGE_ELEMS) rows >>= 1;
+        const double fit = (SPMV_STAGE_ELEMS - 8) / (avg * 1.2 + 0.5);      // 20 % headroom for long-row clusters
+        rows = fit > SPMV_MAX_TILE_ROWS ? SPMV_MAX_TILE_ROWS : (int)fit;
+        rows = rows >= 32 ? (rows / 32) * 32 : (rows < 4 ? 4 : rows);
     }
     return rows;
+}
+
+constexpr int SPMV_NCAND = 12;
+__constant__ int c_spmv_cand[SPMV_NCAND] = {1024, 768, 512, 384, 256, 192, 160, 128, 96, 64, 32, 16};
+
+// max over tiles of the (16-byte padded) staged element count, for every candidate tile height
+__global__ void k_spmv_plan(int64_t n, const int64_t *__restrict__ indptr, int *__restrict__ max_staged) {
+    const int cand = blockIdx.y;
+    const int rows = c_spmv_cand[cand];
+    const int64_t ntiles = (n + rows - 1) / rows;
+    int64_t m = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
+        const int64_t r0 = t * rows, r1 = r0 + rows < n ? r0 + rows : n;
+        const int64_t base = indptr[r0] & ~(int64_t)3, end = (indptr[r1] + 3) & ~(int64_t)3;
+        m = end - base > m ? end - base : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int64_t v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(&max_staged[cand], (int)(m > 0x7fffffff ? 0x7fffffff : m));
 }
 
 inline unsigned spmv_grid(int64_t n, int ctas_per_sm, int rows_per_tile) {
@@ -345,6 +370,30 @@ inline unsigned spmv_grid(int64_t n, int ctas_per_sm, int rows_per_tile) {
 }
 
 }  // namespace
+
+// Exact tile height for a matrix: the tallest candidate whose largest tile still fits one TMA stage
+// (one tiny kernel + one 48-byte read-back; done once per operator, not per SpMV).
+int spmv_plan_rows(int64_t n, const int64_t *indptr, int *rows_out, cudaStream_t st) {
+    Scratch<int> mx(st);
+    MWX_CUDA(mx.alloc(SPMV_NCAND));
+    MWX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int) * SPMV_NCAND, st));
+    int64_t gx = (n / 16 + 255) / 256;
+    if (gx > 512) gx = 512;
+    if (gx < 1) gx = 1;
+    k_spmv_plan<<<dim3((unsigned)gx, SPMV_NCAND), 256, 0, st>>>(n, indptr, mx.p);
+    MWX_LAUNCH_CHECK();
+    int h[SPMV_NCAND];
+    MWX_CUDA(cudaMemcpyAsync(h, mx.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MWX_CUDA(cudaStreamSynchronize(st));
+    static const int cand[SPMV_NCAND] = {1024, 768, 512, 384, 256, 192, 160, 128, 96, 64, 32, 16};
+    int rows = 8;
+    for (int c = 0; c < SPMV_NCAND; ++c)
+        if (h[c] <= SPMV_STAGE_ELEMS) { rows = cand[c]; break; }
+    *rows_out = rows;
+    return 0;
+}
+
+namespace {
 
 template <bool DOT, int MODE>
 int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
@@ -360,12 +409,14 @@ int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *in
     }
     // TMA bulk copies need 16-byte aligned global addresses; the kernel aligns offsets, the bases must be too
     const int tma_ok = (((uintptr_t)values & 15) == 0 && ((uintptr_t)indices & 15) == 0) ? 1 : 0;
-    const int rows = spmv_rows_per_tile(n, nnz);
+    const int rows = nnz <= -8 ? (int)(-nnz) : spmv_rows_per_tile(n, nnz);    // nnz <= -8: planned tile height
     k_spmv<DOT, MODE><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SPMV_SMEM_BYTES, st>>>(
         n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows);
     MWX_LAUNCH_CHECK();
     return 0;
 }
+
+}  // namespace
 
 int launch_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                 const double *x, double *y, const double *dot_with, double *dot_out, double *partials,
@@ -432,8 +483,13 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
     MWX_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
     if (maxiter <= 0) maxiter = 10 * n;
     double h[2];
-    int64_t nnz = -1;
-    MWX_CUDA(cudaMemcpyAsync(&nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    int64_t nnz = -1;                              // SpMV tile height, planned once per solve (encoded as -rows)
+    {
+        int rows = 0;
+        int prc = spmv_plan_rows(n, indptr, &rows, st);
+        if (prc) return prc;
+        nnz = -(int64_t)rows;
+    }
     // ||b|| and r = b - A*0 = b
     int rc = launch_dot(n, b, b, &sc.p->aux, partials.p, &sc.p->ticket[0], st);
     if (rc) return rc;
@@ -495,6 +551,14 @@ extern "C" int mwx_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int
                         const double *values, const double *x, double *y, void *stream) {
     if (n <= 0 || !indptr || !indices || !values || !x || !y) return MWX_E_BADARG;
     return launch_spmv(n, nnz, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int mwx_spmv_plan(int64_t n, const int64_t *indptr, int32_t *tile_rows_host, void *stream) {
+    if (n <= 0 || !indptr || !tile_rows_host) return MWX_E_BADARG;
+    int rows = 0;
+    int rc = spmv_plan_rows(n, indptr, &rows, as_stream(stream));
+    *tile_rows_host = rows;
+    return rc;
 }
 
 extern "C" int mwx_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices,

@@ -16,7 +16,9 @@ struct CgScalars {
 
 constexpr int RED_MAX_BLOCKS = 4096;   // partial-sum slots per reduction site
 
-// `nnz` in the SpMV launchers is a hint (-1 = unknown) used to size the row tiles.
+// `nnz` in the SpMV launchers sizes the row tiles: >= 0 = nonzero count (heuristic), -1 = unknown,
+// <= -8 = -(tile height) from spmv_plan_rows (exact: the tallest tile that always fits a TMA stage).
+int spmv_plan_rows(int64_t n, const int64_t *indptr, int *rows_out, cudaStream_t st);
 // y = A x (CSR, int64 indptr, int32 cols, fp64).  If dot_with != nullptr also accumulates
 // sum_i dot_with[i] * y[i] into *dot_out deterministically (per-CTA partials, last CTA folds them in
 // index order).  partials: RED_MAX_BLOCKS doubles, ticket: zero-initialised counter.

@@ -93,7 +93,7 @@ class AMGHierarchy:
     """
     MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2}
 
-    def __init__(self, A, mode='parity', degree=3, theta=0.25, max_levels=10, max_coarse=10, reorder=None):
+    def __init__(self, A, mode='parity', degree=2, theta=0.25, max_levels=10, max_coarse=10, reorder=None):
         torch = L.require_cuda()
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {list(self.MODES)}")
@@ -131,6 +131,9 @@ class AMGHierarchy:
                                    ctypes.byref(self._dev), L.stream()), 'mwx_amg_upload')
         torch.cuda.synchronize()
         self.upload_seconds = time.perf_counter() - t1
+
+    def set_chebyshev(self, degree=2, ratio=10.0):
+        L.check(L.lib().mwx_amg_set_chebyshev(self._dev, int(degree), float(ratio)), 'mwx_amg_set_chebyshev')
 
     def level_dims(self, level, which=0):
         dims = np.zeros(3, dtype=np.int64)
@@ -270,7 +273,7 @@ def solver_iter_pcg(**kwargs):
     return solver_iter_krylov(**kwargs)
 
 
-def _make_mgcg(print_iters, krylov=None, verbose=False, mode='parity', degree=3, **kwargs):
+def _make_mgcg(print_iters, krylov=None, verbose=False, mode='parity', degree=2, **kwargs):
     if krylov is not None and getattr(krylov, '__name__', 'cg') != 'cg':
         raise NotImplementedError("only conjugate gradients (scipy's cg) has a device implementation")
 
@@ -297,13 +300,13 @@ def _make_mgcg(print_iters, krylov=None, verbose=False, mode='parity', degree=3,
     return solver
 
 
-def solver_iter_mgcg(krylov=None, verbose=False, mode='parity', degree=3, **kwargs):
+def solver_iter_mgcg(krylov=None, verbose=False, mode='parity', degree=2, **kwargs):
     """ref utils.py:127-166: RS-AMG V-cycle preconditioned CG.  ``mode`` selects the smoother
     ('parity' = pyamg's symmetric Gauss-Seidel, 'chebyshev' / 'jacobi' = fast device smoothers)."""
     return _make_mgcg(False, krylov, verbose, mode, degree, **kwargs)
 
 
-def solver_iter_mgcg_iter(krylov=None, verbose=False, mode='parity', degree=3, **kwargs):
+def solver_iter_mgcg_iter(krylov=None, verbose=False, mode='parity', degree=2, **kwargs):
     """ref utils.py:87-125: same, and prints ``mgcg total interation steps: N``."""
     return _make_mgcg(True, krylov, verbose, mode, degree, **kwargs)
 

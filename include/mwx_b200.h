@@ -136,7 +136,9 @@ int mwx_gather_f64(int64_t n, const double *src, const int32_t *idx, double *dst
 /* ------------------------------------------------------------------ SpMV / vector kernels (hot path B)
  * y = A x.  Replaces scipy csr_matvec inside spl.cg  ref main/example1/utils.py:157. */
 int mwx_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
-             const double *values, const double *x, double *y, void *stream);   /* nnz: tiling hint, -1 = unknown */
+             const double *values, const double *x, double *y, void *stream);   /* nnz >= 0: tiling hint, -1 unknown, <= -8: -(tile rows) from mwx_spmv_plan */
+/* Tallest SpMV row tile whose every tile fits one TMA stage; pass -(tile_rows) as `nnz` to mwx_spmv. */
+int mwx_spmv_plan(int64_t n, const int64_t *indptr, int32_t *tile_rows_host, void *stream);
 /* diag[i] = A[i,i] (0 if absent): build_pc_diag, ref main/example1/utils.py:48-50. */
 int mwx_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices,
                      const double *values, double *diag, void *stream);
@@ -184,6 +186,9 @@ typedef struct mwx_amg_dev mwx_amg_dev_t;
  * NULL = computed inside by a symmetric Jacobi eigen-solver with pinv2's cutoff. */
 int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t cheby_degree,
                    const double *coarse_pinv_host, mwx_amg_dev_t **out, void *stream);
+/* Chebyshev smoother: polynomial degree and eigenvalue interval [1.1 rho / ratio, 1.1 rho] (default 2, 10; tuned on the
+ * level-11/12 meshes, profiles/r01_tune_amg.txt). */
+int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ratio);
 /* Estimated spectral radius of D^-1 A on a level (fast-mode smoothers; 0 in parity mode). */
 int mwx_amg_level_rho(const mwx_amg_dev_t *d, int32_t level, double *rho_host);
 void mwx_amg_destroy_dev(mwx_amg_dev_t *d);

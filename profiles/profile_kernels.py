@@ -30,7 +30,7 @@ x = torch.rand(n, dtype=torch.float64, device='cuda')
 y = torch.empty_like(x)
 for _ in range(3):
     K2 = F.asm_gpu(form, basis, out=K2.d_data)
-    L.check(L.lib().mwx_spmv(n, Kc.nnz, L.ptr(Kc.d_indptr), L.ptr(Kc.d_indices), L.ptr(Kc.d_data), L.ptr(x), L.ptr(y), L.stream()))
+    L.check(L.lib().mwx_spmv(n, Kc.spmv_hint(), L.ptr(Kc.d_indptr), L.ptr(Kc.d_indices), L.ptr(Kc.d_data), L.ptr(x), L.ptr(y), L.stream()))
 torch.cuda.synchronize()
 if maxit:
     b = Kc.dot(x)
