@@ -31,7 +31,18 @@ _SIGNATURES = {
     'mwx_pattern_fill': [i64, i64, vp, vp, vp, vp, vp, vp, vp],
     'mwx_assemble_morley': [i64, i64, vp, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp],
     'mwx_assemble_penalty': [i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp, vp],
+    'mwx_assemble_morley_rows': [i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp],
     'mwx_axpby': [i64, f64, vp, f64, vp, vp, vp],
+    'mwx_dist_rows_count': [i64, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_dist_rows_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_dist_localize': [i64, vp, i32, i32, vp, i32, i32, vp, vp],
+    'mwx_gather_f64_i64': [i64, vp, vp, vp, vp],
+    'mwx_dcg_workspace_doubles': [],
+    'mwx_dcg_dot': [i64, vp, vp, vp, i32, vp],
+    'mwx_dcg_p_update': [i64, vp, vp, vp, vp, vp, i32, vp],
+    'mwx_dcg_spmv_dot': [i64, i64, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_dcg_xr_update': [i64, vp, vp, vp, vp, vp, vp, i32, vp],
+    'mwx_dcg_residual': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_condense_count': [i64, vp, vp, vp, vp, vp, _pi64, _pi64, vp],
     'mwx_condense_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_hilbert_keys': [i64, vp, f64, f64, f64, vp, vp],

@@ -155,28 +155,35 @@ __device__ __forceinline__ void morley_local_row(double2 x0, double2 x1, double2
     }
 }
 
+// ROWLIST = false: tile position i is matrix row i and the output is the global CSR (values + indptr).
+// ROWLIST = true : position i is row row_ids[i]; the rows are written back to back through out_indptr
+//                  (nrows + 1 entries) - a rank of the partitioned solver assembles only the rows it owns.
+template <bool ROWLIST>
 __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
-    int64_t ndofs, int64_t nt, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+    int64_t nrows, int64_t nt, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
     const int64_t *__restrict__ r2e_ptr, const int32_t *__restrict__ r2e_idx,
     const unsigned long long *__restrict__ slot8, const int64_t *__restrict__ indptr,
+    const int32_t *__restrict__ row_ids, const int64_t *__restrict__ out_indptr,
     double ca, double cb, int accumulate, double *__restrict__ values) {
     __shared__ double acc[ASM_CAP];
-    const int64_t r0 = (int64_t)blockIdx.x * ASM_ROWS;
-    const int64_t r1 = r0 + ASM_ROWS < ndofs ? r0 + ASM_ROWS : ndofs;
-    const int64_t s0 = indptr[r0], s1 = indptr[r1];
+    const int64_t *optr = ROWLIST ? out_indptr : indptr;
+    const int64_t i0 = (int64_t)blockIdx.x * ASM_ROWS;
+    const int64_t i1 = i0 + ASM_ROWS < nrows ? i0 + ASM_ROWS : nrows;
+    const int64_t s0 = optr[i0], s1 = optr[i1];
     const int64_t len = s1 - s0;
     const bool staged = len <= ASM_CAP;          // CTA-uniform
-    const int64_t r = r0 + threadIdx.x;
+    const int64_t i = i0 + threadIdx.x;
 
     if (staged) {
         for (int k = threadIdx.x; k < (int)len; k += ASM_ROWS) acc[k] = 0.0;
         __syncthreads();
     }
-    if (r < r1) {
-        const int64_t rs = indptr[r];
+    if (i < i1) {
+        const int64_t r = ROWLIST ? (int64_t)row_ids[i] : i;
+        const int64_t rs = optr[i];
         double *dst = staged ? acc + (rs - s0) : values + rs;
         if (!staged && !accumulate) {
-            const int64_t re = indptr[r + 1];
+            const int64_t re = optr[i + 1];
             for (int64_t k = rs; k < re; ++k) values[k] = 0.0;
         }
         const int64_t pb = r2e_ptr[r], pe = r2e_ptr[r + 1];
@@ -201,7 +208,6 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
             for (int k = threadIdx.x; k < (int)len; k += ASM_ROWS) values[s0 + k] = acc[k];
     }
 }
-
 
 // ------------------------------------------------------------------ boundary-facet penalty terms
 // Row i of  c1*penalty_1 + c2*penalty_2 + c3*penalty_3  (ref main/example1/run.py:134-146) for the
@@ -347,9 +353,24 @@ extern "C" int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy,
         return MWX_E_BADARG;
     if (((uintptr_t)slot8 & 7) || ((uintptr_t)pxy & 15)) return MWX_E_BADARG;
     const unsigned grid = (unsigned)((ndofs + ASM_ROWS - 1) / ASM_ROWS);
-    k_assemble_morley<<<grid, ASM_ROWS, 0, as_stream(stream)>>>(
-        ndofs, nt, (const double2 *)pxy, t, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr,
-        ca, cb, accumulate, values);
+    k_assemble_morley<false><<<grid, ASM_ROWS, 0, as_stream(stream)>>>(
+        ndofs, nt, (const double2 *)pxy, t, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, nullptr,
+        nullptr, ca, cb, accumulate, values);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_assemble_morley_rows(int64_t nrows, const int32_t *row_ids, const int64_t *out_indptr,
+                                        int64_t nt, const double *pxy, const int32_t *t, const int64_t *r2e_ptr,
+                                        const int32_t *r2e_idx, const uint8_t *slot8, const int64_t *indptr,
+                                        double ca, double cb, double *values, void *stream) {
+    if (nrows < 0 || nt <= 0 || !pxy || !t || !r2e_ptr || !r2e_idx || !slot8 || !indptr || !values) return MWX_E_BADARG;
+    if (nrows == 0) return 0;
+    if (!row_ids || !out_indptr || ((uintptr_t)slot8 & 7) || ((uintptr_t)pxy & 15)) return MWX_E_BADARG;
+    const unsigned grid = (unsigned)((nrows + ASM_ROWS - 1) / ASM_ROWS);
+    k_assemble_morley<true><<<grid, ASM_ROWS, 0, as_stream(stream)>>>(
+        nrows, nt, (const double2 *)pxy, t, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, row_ids,
+        out_indptr, ca, cb, 0, values);
     MWX_LAUNCH_CHECK();
     return 0;
 }

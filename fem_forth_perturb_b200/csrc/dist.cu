@@ -1,0 +1,139 @@
+// Row-block partitioned systems: local-matrix planning for one rank, and the CG building
+// blocks the multi-GPU driver (fem_forth_perturb_b200/dist.py) chains between its halo exchanges and
+// all-reduces.  Nothing here has a reference counterpart - the reference is one CPU process.
+//
+// A rank owns a contiguous range [lo, hi) of the (partition, Hilbert)-ordered condensed DOFs.  Its local
+// operator is built from the rows it assembled itself (mwx_assemble_morley_rows): Dirichlet columns are
+// dropped, the rest renumbered to the global solver numbering and then to [owned | ghost] local indices.
+#include "krylov.cuh"
+
+namespace mwx {
+namespace {
+
+constexpr int DIST_MAX_ROW = 256;
+
+__global__ void k_dist_rows_count(int64_t nloc, const int32_t *__restrict__ rows, const int64_t *__restrict__ indptr,
+                                  const int32_t *__restrict__ indices, const int32_t *__restrict__ gid,
+                                  int32_t *__restrict__ raw_len, int32_t *__restrict__ kept_len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nloc) return;
+    const int64_t r = rows[i];
+    int c = 0;
+    for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k) c += gid[indices[k]] >= 0;
+    raw_len[i] = (int32_t)(indptr[r + 1] - indptr[r]);
+    kept_len[i] = c;
+}
+
+// cols_g: global solver ids, ascending per row; src: where the value sits in the raw assembled rows.
+__global__ void __launch_bounds__(128) k_dist_rows_fill(int64_t nloc, const int32_t *__restrict__ rows,
+                                                        const int64_t *__restrict__ indptr,
+                                                        const int32_t *__restrict__ indices,
+                                                        const int32_t *__restrict__ gid,
+                                                        const int64_t *__restrict__ raw_indptr,
+                                                        const int64_t *__restrict__ loc_indptr,
+                                                        int32_t *__restrict__ cols_g, int64_t *__restrict__ src,
+                                                        int32_t *__restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nloc) return;
+    const int64_t r = rows[i];
+    const int64_t s = indptr[r], len = indptr[r + 1] - s;
+    if (len > DIST_MAX_ROW) { atomicExch(err, 1); return; }
+    int32_t c[DIST_MAX_ROW];
+    int32_t o[DIST_MAX_ROW];
+    int n = 0;
+    for (int k = 0; k < (int)len; ++k) {
+        const int32_t g = gid[indices[s + k]];
+        if (g < 0) continue;
+        int j = n - 1;
+        while (j >= 0 && c[j] > g) { c[j + 1] = c[j]; o[j + 1] = o[j]; --j; }
+        c[j + 1] = g; o[j + 1] = k;
+        ++n;
+    }
+    const int64_t d = loc_indptr[i], rb = raw_indptr[i];
+    for (int k = 0; k < n; ++k) { cols_g[d + k] = c[k]; src[d + k] = rb + o[k]; }
+}
+
+__global__ void k_dist_localize(int64_t nnz, const int32_t *__restrict__ cols_g, int32_t lo, int32_t hi,
+                                const int32_t *__restrict__ ghosts, int32_t nghost, int32_t nloc,
+                                int32_t *__restrict__ cols_l) {
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += st) {
+        const int32_t g = cols_g[k];
+        if (g >= lo && g < hi) { cols_l[k] = g - lo; continue; }
+        int32_t a = 0, b = nghost - 1;
+        while (a < b) {
+            const int32_t m = (a + b) >> 1;
+            if (ghosts[m] < g) a = m + 1; else b = m;
+        }
+        cols_l[k] = nloc + a;
+    }
+}
+
+__global__ void k_gather_f64_i64(int64_t n, const double *__restrict__ src, const int64_t *__restrict__ idx,
+                                 double *__restrict__ dst) {
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st) dst[i] = src[idx[i]];
+}
+
+inline unsigned sgrid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+}  // namespace mwx
+
+using namespace mwx;
+
+extern "C" int mwx_dist_rows_count(int64_t nloc, const int32_t *rows, const int64_t *indptr,
+                                   const int32_t *indices, const int32_t *gid, int64_t *raw_indptr,
+                                   int64_t *loc_indptr, void *stream) {
+    if (nloc <= 0 || !rows || !indptr || !indices || !gid || !raw_indptr || !loc_indptr) return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    Scratch<int32_t> raw(st), kept(st);
+    MWX_CUDA(raw.alloc((size_t)nloc));
+    MWX_CUDA(kept.alloc((size_t)nloc));
+    k_dist_rows_count<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, rows, indptr, indices, gid, raw.p, kept.p);
+    MWX_LAUNCH_CHECK();
+    int rc = exclusive_scan_i32_to_i64(raw.p, nloc, raw_indptr, st);
+    if (rc) return rc;
+    return exclusive_scan_i32_to_i64(kept.p, nloc, loc_indptr, st);
+}
+
+extern "C" int mwx_dist_rows_fill(int64_t nloc, const int32_t *rows, const int64_t *indptr,
+                                  const int32_t *indices, const int32_t *gid, const int64_t *raw_indptr,
+                                  const int64_t *loc_indptr, int32_t *cols_g, int64_t *src, void *stream) {
+    if (nloc <= 0 || !rows || !indptr || !indices || !gid || !raw_indptr || !loc_indptr || !cols_g || !src)
+        return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    Scratch<int32_t> err(st);
+    MWX_CUDA(err.alloc(1));
+    MWX_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int32_t), st));
+    k_dist_rows_fill<<<grid_for(nloc, 128), 128, 0, st>>>(nloc, rows, indptr, indices, gid, raw_indptr, loc_indptr,
+                                                         cols_g, src, err.p);
+    MWX_LAUNCH_CHECK();
+    int32_t h = 0;
+    MWX_CUDA(cudaMemcpyAsync(&h, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MWX_CUDA(cudaStreamSynchronize(st));
+    return h ? MWX_E_CAPACITY : 0;
+}
+
+extern "C" int mwx_dist_localize(int64_t nnz, const int32_t *cols_g, int32_t lo, int32_t hi,
+                                 const int32_t *ghosts, int32_t nghost, int32_t nloc, int32_t *cols_l,
+                                 void *stream) {
+    if (nnz < 0 || (nnz && (!cols_g || !cols_l)) || (nghost && !ghosts)) return MWX_E_BADARG;
+    if (nnz == 0) return 0;
+    k_dist_localize<<<sgrid(nnz), 256, 0, as_stream(stream)>>>(nnz, cols_g, lo, hi, ghosts, nghost, nloc, cols_l);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *idx, double *dst, void *stream) {
+    if (n < 0 || (n && (!src || !idx || !dst))) return MWX_E_BADARG;
+    if (n == 0) return 0;
+    k_gather_f64_i64<<<sgrid(n), 256, 0, as_stream(stream)>>>(n, src, idx, dst);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}

@@ -584,3 +584,51 @@ extern "C" int mwx_pcg_jacobi(int64_t n, const int64_t *indptr, const int32_t *i
     return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, precondition ? dinv : nullptr,
                     nullptr, nullptr, r, nullptr, p, q, iters_host, info_host, resid_host, st);
 }
+
+// ------------------------------------------------------------------ building blocks for the partitioned CG
+// The multi-GPU driver keeps one workspace per rank: ws[0..4] = {rho, rho_prev, pq, rr, aux} (the
+// CgScalars doubles; ws[5..7] hold its counters and must not be touched), ws[8..] = reduction partials.
+// Every kernel below leaves LOCAL partial sums in the scalar slots; the driver all-reduces them.
+static inline CgScalars *ws_scalars(double *ws) { return reinterpret_cast<CgScalars *>(ws); }
+static inline double *ws_partials(double *ws) { return ws + 8; }
+
+extern "C" int mwx_dcg_workspace_doubles(void) { return 8 + 2 * RED_MAX_BLOCKS; }
+
+extern "C" int mwx_dcg_dot(int64_t n, const double *a, const double *b, double *ws, int32_t slot, void *stream) {
+    if (n <= 0 || !a || !b || !ws || slot < 0 || slot > 4) return MWX_E_BADARG;
+    CgScalars *sc = ws_scalars(ws);
+    return launch_dot(n, a, b, reinterpret_cast<double *>(sc) + slot, ws_partials(ws), &sc->ticket[0], as_stream(stream));
+}
+
+extern "C" int mwx_dcg_p_update(int64_t n, const double *r, const double *dinv, const double *z, double *p,
+                                double *ws, int32_t first, void *stream) {
+    if (n <= 0 || !p || !ws || (!z && !r)) return MWX_E_BADARG;
+    k_p_update<<<vec_grid(n), VEC_THREADS, 0, as_stream(stream)>>>(n, r, dinv, z, p, ws_scalars(ws), first);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_dcg_spmv_dot(int64_t n, int64_t nnz_hint, const int64_t *indptr, const int32_t *indices,
+                                const double *values, const double *x_ext, double *q, double *ws, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x_ext || !q || !ws) return MWX_E_BADARG;
+    CgScalars *sc = ws_scalars(ws);
+    // x_ext = [owned | ghosts]; the first n entries are the owned p used in p.Ap
+    return launch_spmv(n, nnz_hint, indptr, indices, values, x_ext, q, x_ext, &sc->pq, ws_partials(ws), &sc->ticket[0],
+                       as_stream(stream));
+}
+
+extern "C" int mwx_dcg_xr_update(int64_t n, const double *p, const double *q, double *x, double *r,
+                                 const double *dinv, double *ws, int32_t jacobi, void *stream) {
+    if (n <= 0 || !p || !q || !x || !r || !ws) return MWX_E_BADARG;
+    k_xr_update<<<vec_grid(n), VEC_THREADS, 0, as_stream(stream)>>>(n, p, q, x, r, dinv, ws_scalars(ws), ws_partials(ws),
+                                                                    jacobi ? 1 : 0);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_dcg_residual(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                                const double *x_ext, const double *b, double *r, const double *dinv, double *ws,
+                                void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x_ext || !b || !r || !ws) return MWX_E_BADARG;
+    return launch_residual(n, indptr, indices, values, x_ext, b, r, dinv, ws_scalars(ws), ws_partials(ws), as_stream(stream));
+}

@@ -107,6 +107,14 @@ int mwx_assemble_penalty(int64_t nt, int64_t nbf, const double *pxy, const int32
 int mwx_axpby(int64_t n, double alpha, const double *a, double beta, const double *b,
               double *out, void *stream);
 
+/* Same kernel for a row subset (partitioned assembly, SURVEY 8e: every rank assembles the rows it owns, no
+ * communication): row_ids (nrows) lists matrix rows, the rows are written back to back through out_indptr
+ * (nrows+1; out_indptr[i+1]-out_indptr[i] = length of row row_ids[i] in the global pattern). */
+int mwx_assemble_morley_rows(int64_t nrows, const int32_t *row_ids, const int64_t *out_indptr, int64_t nt,
+                             const double *pxy, const int32_t *t, const int64_t *r2e_ptr,
+                             const int32_t *r2e_idx, const uint8_t *slot8, const int64_t *indptr,
+                             double ca, double cb, double *values, void *stream);
+
 /* ------------------------------------------------------------------ condense (glue A -> B)
  * Replaces condense(K2, f2, D=...) ref main/example1/utils.py:384-460:
  *   Aout = A[I].T[I].T,  bout = b[I] - A[I].T[D].T @ x[D].
@@ -199,6 +207,36 @@ int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_
                 const double *values, const double *b, double *x, double tol, int64_t maxiter,
                 double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
                 void *stream);
+
+/* ------------------------------------------------------------------ partitioned solve (no reference counterpart)
+ * A rank owns the contiguous range [lo, hi) of the solver numbering.  gid (ndofs) maps a skfem DOF to its
+ * solver id, or -1 for an eliminated (Dirichlet) DOF.  rows (nloc) = skfem ids of the owned DOFs in solver order.
+ * Pass 1: raw_indptr (rows as assembled by mwx_assemble_morley_rows) and loc_indptr (Dirichlet columns dropped). */
+int mwx_dist_rows_count(int64_t nloc, const int32_t *rows, const int64_t *indptr, const int32_t *indices,
+                        const int32_t *gid, int64_t *raw_indptr, int64_t *loc_indptr, void *stream);
+/* Pass 2: cols_g = solver ids (ascending per row), src = position of each kept value in the raw rows. */
+int mwx_dist_rows_fill(int64_t nloc, const int32_t *rows, const int64_t *indptr, const int32_t *indices,
+                       const int32_t *gid, const int64_t *raw_indptr, const int64_t *loc_indptr,
+                       int32_t *cols_g, int64_t *src, void *stream);
+/* Local column ids: owned g -> g - lo, otherwise nloc + rank of g in the sorted ghost list. */
+int mwx_dist_localize(int64_t nnz, const int32_t *cols_g, int32_t lo, int32_t hi, const int32_t *ghosts,
+                      int32_t nghost, int32_t nloc, int32_t *cols_l, void *stream);
+int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *idx, double *dst, void *stream);
+
+/* CG building blocks chained by the multi-GPU driver between halo exchanges and all-reduces.  ws: zero-initialised
+ * workspace of mwx_dcg_workspace_doubles() doubles; ws[0..4] = {rho, rho_prev, pq, rr, aux}.  Kernels leave LOCAL
+ * partial sums there (deterministic per rank); the driver all-reduces them.  x_ext = [owned | ghost] vector. */
+int mwx_dcg_workspace_doubles(void);
+int mwx_dcg_dot(int64_t n, const double *a, const double *b, double *ws, int32_t slot, void *stream);
+int mwx_dcg_p_update(int64_t n, const double *r, const double *dinv, const double *z, double *p, double *ws,
+                     int32_t first, void *stream);               /* p = z + (rho/rho_prev) p;  z NULL -> dinv .* r */
+int mwx_dcg_spmv_dot(int64_t n, int64_t nnz_hint, const int64_t *indptr, const int32_t *indices,
+                     const double *values, const double *x_ext, double *q, double *ws, void *stream);  /* pq */
+int mwx_dcg_xr_update(int64_t n, const double *p, const double *q, double *x, double *r, const double *dinv,
+                      double *ws, int32_t jacobi, void *stream);   /* alpha = rho/pq; rr (and rho if jacobi) */
+int mwx_dcg_residual(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                     const double *x_ext, const double *b, double *r, const double *dinv, double *ws,
+                     void *stream);                                /* r = b - A x; rr, rho */
 
 #ifdef __cplusplus
 }
