@@ -49,6 +49,10 @@ _SIGNATURES = {
     'mwx_csr_permute': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_gather_f64': [i64, vp, vp, vp, vp],
     'mwx_spmv': [i64, i64, vp, vp, vp, vp, vp, vp],
+    'mwx_spmv_axpy': [i64, i64, vp, vp, vp, vp, vp, i32, vp, vp],
+    'mwx_smoother_step': [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, f64, vp],
+    'mwx_smoother_first': [i64, vp, vp, f64, vp, vp, vp],
+    'mwx_dense_gemv': [i64, vp, vp, vp, vp],
     'mwx_spmv_plan': [i64, vp, _pi32, vp],
     'mwx_csr_diagonal': [i64, vp, vp, vp, vp, vp],
     'mwx_pcg_jacobi': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp],

@@ -453,6 +453,21 @@ extern "C" int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, c
                     iters_host, info_host, resid_host, as_stream(stream));
 }
 
+extern "C" int mwx_smoother_first(int64_t n, const double *b, const double *dinv, double c2, double *x, double *d,
+                                  void *stream) {
+    if (n <= 0 || !b || !dinv || !x || !d) return MWX_E_BADARG;
+    k_cheby_first_zero<<<vgrid(n), 256, 0, as_stream(stream)>>>(n, b, dinv, c2, x, d);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_dense_gemv(int64_t n, const double *M, const double *v, double *out, void *stream) {
+    if (n <= 0 || !M || !v || !out) return MWX_E_BADARG;
+    k_dense_gemv<<<grid_for(n * 32, 256), 256, 0, as_stream(stream)>>>(n, M, v, out);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ratio) {
     if (!d || degree < 1 || degree > 16 || !(ratio > 1.0)) return MWX_E_BADARG;
     d->degree = degree;

@@ -553,6 +553,21 @@ extern "C" int mwx_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int
     return launch_spmv(n, nnz, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
 }
 
+extern "C" int mwx_spmv_axpy(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                             const double *values, const double *x, const double *c, int32_t sign, double *y,
+                             void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x || !c || !y || sign == 0) return MWX_E_BADARG;
+    return launch_spmv_axpy(n, nnz, indptr, indices, values, x, y, c, sign, as_stream(stream));
+}
+
+extern "C" int mwx_smoother_step(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                                 const double *values, const double *x_in, double *x_out, const double *b,
+                                 const double *dinv, double *d, double c1, double c2, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x_in || !x_out || !b || !dinv || !d || x_in == x_out)
+        return MWX_E_BADARG;
+    return launch_smoother_step(n, nnz, indptr, indices, values, x_in, x_out, b, dinv, d, c1, c2, as_stream(stream));
+}
+
 extern "C" int mwx_spmv_plan(int64_t n, const int64_t *indptr, int32_t *tile_rows_host, void *stream) {
     if (n <= 0 || !indptr || !tile_rows_host) return MWX_E_BADARG;
     int rows = 0;

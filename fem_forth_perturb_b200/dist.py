@@ -72,7 +72,56 @@ class Partition:
 
 
 # ------------------------------------------------------------------------------------------ one rank's block
-class RankSystem:
+class HaloPlan:
+    """Column side of a row-block operator: owned columns [clo, clo + ncol) then `ghosts` (sorted global ids)."""
+
+    def _plan_ghosts(self, col_offsets, device):
+        torch = L.require_cuda()
+        offs = torch.tensor(col_offsets[1:], dtype=torch.int32, device=device)
+        owner = torch.searchsorted(offs, self.ghosts, right=True).cpu().numpy()
+        self.recv = {}                                   # owner -> (start, count) inside the ghost segment
+        for peer in np.unique(owner):
+            sel = np.nonzero(owner == peer)[0]
+            self.recv[int(peer)] = (int(sel[0]), int(len(sel)))
+        self.send = {}                                   # peer -> local owned indices it needs (device int32)
+
+    def requests(self):
+        """{owner: global ids this rank needs from it}."""
+        return {peer: self.ghosts[s:s + c] for peer, (s, c) in self.recv.items()}
+
+    def set_send_lists(self, asked):
+        """asked: {peer: global ids (device) that peer needs from this rank}."""
+        for peer, ids in asked.items():
+            self.send[peer] = (ids - self.clo).to(L.require_cuda().int32).contiguous()
+
+
+class LocalOp(HaloPlan):
+    """Rows [rlo, rhi) of a global CSR operator (device tensors), columns renumbered to [owned | ghost]."""
+
+    def __init__(self, indptr, indices, values, rlo, rhi, col_offsets, rank):
+        torch = L.require_cuda()
+        dev = values.device
+        self.rank, self.nloc = rank, rhi - rlo
+        self.clo, self.ncol = col_offsets[rank], col_offsets[rank + 1] - col_offsets[rank]
+        s0, s1 = int(indptr[rlo].item()), int(indptr[rhi].item())
+        self.indptr = (indptr[rlo:rhi + 1] - s0).contiguous()
+        cols_g = indices[s0:s1].contiguous()
+        self.vals = values[s0:s1].clone()
+        self.nnz = s1 - s0
+        off = (cols_g < self.clo) | (cols_g >= self.clo + self.ncol)
+        self.ghosts = torch.unique(cols_g[off]).to(torch.int32).contiguous()
+        self.nghost = int(self.ghosts.numel())
+        self.cols = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+        L.check(L.lib().mwx_dist_localize(self.nnz, L.ptr(cols_g), self.clo, self.clo + self.ncol, L.ptr(self.ghosts),
+                                          self.nghost, self.ncol, L.ptr(self.cols), L.stream()), 'mwx_dist_localize')
+        rows_plan = ctypes.c_int32(0)
+        if self.nloc > 0:
+            L.check(L.lib().mwx_spmv_plan(self.nloc, L.ptr(self.indptr), ctypes.byref(rows_plan), L.stream()), 'mwx_spmv_plan')
+        self.spmv_hint = -int(rows_plan.value) if rows_plan.value else -1
+        self._plan_ghosts(col_offsets, dev)
+
+
+class RankSystem(HaloPlan):
     """Local operator of one rank: rows [lo, hi) of the solver-numbered K2c, columns = [owned | ghost]."""
 
     def __init__(self, basis, cplan, partition, rank):
@@ -83,6 +132,7 @@ class RankSystem:
         self.basis, self.rank, self.partition = basis, rank, partition
         self.lo, self.hi = partition.offsets[rank], partition.offsets[rank + 1]
         self.nloc = self.hi - self.lo
+        self.clo, self.ncol = self.lo, self.nloc
         I_dev = torch.from_numpy(np.ascontiguousarray(cplan.I, dtype=np.int64)).to(dev)
         gid = torch.full((basis.N,), -1, dtype=torch.int32, device=dev)
         gid[I_dev] = partition.iperm                                        # skfem DOF -> solver id
@@ -109,22 +159,7 @@ class RankSystem:
         L.check(lib.mwx_spmv_plan(self.nloc, L.ptr(self.indptr), ctypes.byref(rows_plan), st), 'mwx_spmv_plan')
         self.spmv_hint = -int(rows_plan.value)
         # ghost ownership: sorted ghosts are grouped by owner because ownership ranges are contiguous
-        offs = torch.tensor(partition.offsets[1:], dtype=torch.int32, device=dev)
-        owner = torch.searchsorted(offs, self.ghosts, right=True).cpu().numpy()
-        self.recv = {}                                                       # peer -> (start, count) in the ghost segment
-        for peer in np.unique(owner):
-            sel = np.nonzero(owner == peer)[0]
-            self.recv[int(peer)] = (int(sel[0]), int(len(sel)))
-        self.send = {}                                                       # peer -> local indices (device int32)
-
-    def requests(self):
-        """{owner: global ids this rank needs from it}."""
-        return {peer: self.ghosts[s:s + c] for peer, (s, c) in self.recv.items()}
-
-    def set_send_lists(self, asked):
-        """asked: {peer: global ids (device) that peer needs from this rank}."""
-        for peer, ids in asked.items():
-            self.send[peer] = (ids - self.lo).to(L.require_cuda().int32).contiguous()
+        self._plan_ghosts(partition.offsets, dev)
 
     def assemble(self, form):
         """Hot path A for this rank: its own rows of K2 (closed-form kernel), then the local value layout."""
@@ -186,7 +221,7 @@ class InProcessComm:
         for p, v in zip(parts, vecs):
             for owner, (s, c) in p.recv.items():
                 po, vo = by_rank[owner]
-                v[p.nloc + s:p.nloc + s + c] = vo[:po.nloc][po.send[p.rank].long()]
+                v[p.ncol + s:p.ncol + s + c] = vo[:po.ncol][po.send[p.rank].long()]
 
     def allreduce_sum(self, tensors):
         total = tensors[0].clone()
@@ -194,6 +229,19 @@ class InProcessComm:
             total += t.to(total.device)
         for t in tensors:
             t.copy_(total)
+
+    def allgather(self, vecs, offsets):
+        """Every part gets the concatenation of all owned segments."""
+        import torch
+        full = torch.cat(vecs)
+        return [full for _ in vecs]
+
+    def is_root(self):
+        return True
+
+    def broadcast_tensors(self, tensors):
+        """Root's list of device tensors (None elsewhere) -> the same list on every rank."""
+        return tensors
 
 
 class TorchDistComm:
@@ -235,10 +283,10 @@ class TorchDistComm:
         (p,), (v,) = parts, vecs
         ops = []
         for owner, (s, c) in p.recv.items():
-            ops.append(self.dist.P2POp(self.dist.irecv, v[p.nloc + s:p.nloc + s + c], owner, group=self.group))
+            ops.append(self.dist.P2POp(self.dist.irecv, v[p.ncol + s:p.ncol + s + c], owner, group=self.group))
         for peer, idx in p.send.items():
             buf = p._sendbuf[peer]
-            p.ops.gather(v, idx, buf)
+            CudaOps.gather(None, v, idx, buf) if getattr(p, 'ops', None) is None else p.ops.gather(v, idx, buf)
             ops.append(self.dist.P2POp(self.dist.isend, buf, peer, group=self.group))
         if ops:
             for w in self.dist.batch_isend_irecv(ops):
@@ -247,6 +295,32 @@ class TorchDistComm:
     def allreduce_sum(self, tensors):
         (t,) = tensors
         self.dist.all_reduce(t, group=self.group)
+
+    def allgather(self, vecs, offsets):
+        import torch
+        (v,) = vecs
+        sizes = [offsets[r + 1] - offsets[r] for r in range(self.world)]
+        m = max(sizes)
+        pad = torch.zeros(m, dtype=v.dtype, device=v.device)
+        pad[:v.numel()] = v
+        out = torch.empty(self.world * m, dtype=v.dtype, device=v.device)
+        self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        return [torch.cat([out[r * m:r * m + sizes[r]] for r in range(self.world)])]
+
+    def is_root(self):
+        return self.rank == 0
+
+    def broadcast_tensors(self, tensors):
+        import torch
+        dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        meta = [[(tuple(t.shape), str(t.dtype)) for t in tensors]] if self.is_root() else [None]
+        self.dist.broadcast_object_list(meta, src=0, group=self.group)
+        out = []
+        for i, (shape, dt) in enumerate(meta[0]):
+            t = tensors[i].contiguous() if self.is_root() else torch.empty(shape, dtype=getattr(torch, dt.split('.')[-1]), device=dev)
+            self.dist.broadcast(t, src=0, group=self.group)
+            out.append(t)
+        return out
 
 
 # ------------------------------------------------------------------------------------------ kernels behind the driver
@@ -293,13 +367,27 @@ class CudaOps:
         L.check(L.lib().mwx_spmv(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_ext),
                                  L.ptr(y), L.stream()), 'mwx_spmv')
 
+    def spmv_axpy(self, p, x_ext, c, sign, y):
+        L.check(L.lib().mwx_spmv_axpy(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_ext),
+                                      L.ptr(c), int(sign), L.ptr(y), L.stream()), 'mwx_spmv_axpy')
+
+    def smoother_first(self, n, b, dinv, c2, x_ext, d):
+        L.check(L.lib().mwx_smoother_first(n, L.ptr(b), L.ptr(dinv), float(c2), L.ptr(x_ext), L.ptr(d), L.stream()),
+                'mwx_smoother_first')
+
+    def smoother_step(self, p, x_in, x_out, b, dinv, d, c1, c2):
+        L.check(L.lib().mwx_smoother_step(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_in),
+                                          L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2), L.stream()),
+                'mwx_smoother_step')
+
 
 # ------------------------------------------------------------------------------------------ the partitioned PCG
 def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=None, ops=None):
     """scipy-1.4.1-semantics PCG on the row-block partitioned system.
 
     parts: this process's RankSystem-like blocks; b_list: their right-hand sides (owned entries, solver order);
-    precond: 'jacobi' | 'none' | 'amg' (block-Jacobi: amg[i].precondition applied to parts[i]'s residual).
+    precond: 'jacobi' | 'none' | 'amg'; amg = a :class:`DistAMG` (global hierarchy, collective V-cycle) or a list of
+    per-part AMGHierarchy objects (block-Jacobi: each rank preconditions with its own diagonal block).
     Returns (x_list, iters, info, resid)."""
     ops = ops or CudaOps()
     n_global = parts[0].partition.n
@@ -336,8 +424,9 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
     resid = bnrm
     for it in range(1, maxiter + 1):
         if not jacobi:
-            for i, (p, st) in enumerate(zip(parts, S)):
-                st['z'] = amg[i].precondition(st['r'])
+            zs = amg.apply([st['r'] for st in S]) if hasattr(amg, 'apply') else [h.precondition(st['r']) for h, st in zip(amg, S)]
+            for p, st, z in zip(parts, S, zs):
+                st['z'] = z
                 ops.dot(p.nloc, st['r'], st['z'], st['ws'], SLOT_RHO)
             reduce_slots([SLOT_RHO])
         for p, st in zip(parts, S):
@@ -386,3 +475,199 @@ class PartitionedProblem:
         for p in self.parts:
             p.assemble(form)
         return self
+
+
+# ------------------------------------------------------------------------------------------ distributed AMG V-cycle
+class BlockJacobiAMG:
+    """Each rank preconditions with the single-GPU V-cycle of its own diagonal block (no communication; the
+    iteration count grows with the number of blocks because the coarse correction stops at the cuts)."""
+
+    def __init__(self, hierarchies):
+        self.h = hierarchies
+
+    def apply(self, r_list):
+        return [h.precondition(r) for h, r in zip(self.h, r_list)]
+
+
+class DistAMG:
+    """The GLOBAL Ruge-Stueben hierarchy (same C++ host setup as the single-GPU solver, built once on the root
+    rank from the solver-numbered matrix) applied as a collective V(1,1) cycle.
+
+    Levels with more than ``switch_rows`` rows are row-blocked like the fine matrix (coarse DOFs inherit the owner
+    of their C point, so every level's ownership ranges stay contiguous); A_l, P_l, R_l each get their own
+    [owned | ghost] column numbering and halo plan.  From the first level at or below ``switch_rows`` on, the
+    residual is all-gathered and every rank runs the remaining levels redundantly with the single-GPU V-cycle.
+    Smoother = Chebyshev (fast mode); iteration counts match the single-GPU fast mode to round-off."""
+
+    def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=60000,
+                 max_levels=10, ops=None):
+        torch = L.require_cuda()
+        from .solvers import AMGHierarchy
+        from .assembly import DeviceCSR
+        if mode != 'chebyshev':
+            raise NotImplementedError("the partitioned V-cycle implements the Chebyshev smoother")
+        self.parts, self.comm, self.ops = parts, comm, ops or CudaOps()
+        self.degree, self.ratio = int(degree), float(ratio)
+        dev = parts[0].vals.device
+        world = comm.world
+        offsets0 = parts[0].partition.offsets
+        # ---- root: host hierarchy of the global matrix, shipped level by level
+        payload, meta = None, None
+        if comm.is_root():
+            host = AMGHierarchy(global_matrix() if callable(global_matrix) else global_matrix, mode='chebyshev',
+                                max_levels=max_levels, reorder=False, upload=False)
+            self.setup_host_seconds = host.setup_host_seconds
+            sizes = host.level_sizes()
+            nl = len(sizes)
+            lsw = nl - 1
+            for l in range(1, nl):
+                if sizes[l] <= switch_rows:
+                    lsw = l
+                    break
+            offs = [list(offsets0)]
+            for l in range(lsw):
+                csum = np.concatenate(([0], np.cumsum(host.splitting(l))))
+                offs.append([int(csum[o]) for o in offs[l]])
+            payload = [torch.tensor([nl, lsw] + [o for lv in offs for o in lv], dtype=torch.int64, device=dev)]
+
+            def put(M):
+                payload.extend([torch.from_numpy(M.indptr.astype(np.int64)).to(dev),
+                                torch.from_numpy(M.indices.astype(np.int32)).to(dev),
+                                torch.from_numpy(M.data.astype(np.float64)).to(dev)])
+            for l in range(lsw):
+                if l > 0:
+                    put(host.level_matrix(l, 0))
+                put(host.level_matrix(l, 1))
+                put(host.level_matrix(l, 2))
+            put(host.level_matrix(lsw, 0))
+            del host
+        payload = comm.broadcast_tensors(payload)
+        head = payload[0].cpu().numpy()
+        nl, lsw = int(head[0]), int(head[1])
+        offs = [list(map(int, head[2 + l * (world + 1):2 + (l + 1) * (world + 1)])) for l in range(lsw + 1)]
+        self.nlevels, self.lsw, self.offsets = nl, lsw, offs
+        it = iter(payload[1:])
+        trip = lambda: (next(it), next(it), next(it))
+        self.levels = []
+        for l in range(lsw):
+            A_full = trip() if l > 0 else None
+            P_full, R_full = trip(), trip()
+            lv = dict(A=[], P=[], R=[])
+            for p in parts:
+                r = p.rank
+                lv['A'].append(p if l == 0 else LocalOp(*A_full, offs[l][r], offs[l][r + 1], offs[l], r))
+                lv['P'].append(LocalOp(*P_full, offs[l][r], offs[l][r + 1], offs[l + 1], r))
+                lv['R'].append(LocalOp(*R_full, offs[l + 1][r], offs[l + 1][r + 1], offs[l], r))
+            for key in ('A', 'P', 'R'):
+                if not (key == 'A' and l == 0):
+                    comm.exchange_requests(lv[key])
+            self.levels.append(lv)
+            del A_full, P_full, R_full
+        A_sw = trip()
+        n_sw = A_sw[0].numel() - 1
+        tail = DeviceCSR(A_sw[0], A_sw[1], A_sw[2], (n_sw, n_sw))
+        self.tail = AMGHierarchy(tail, mode='chebyshev', degree=self.degree, max_levels=max(1, max_levels - lsw),
+                                 reorder=False)
+        self.tail.set_chebyshev(self.degree, self.ratio)
+        # ---- per level work vectors, inverse diagonals, spectral radius estimates
+        ops = self.ops
+        for l, lv in enumerate(self.levels):
+            lv['dinv'] = [ops.diag_inv(a) for a in lv['A']]
+            lv['xa'] = [ops.zeros(a.ncol + a.nghost, dev) for a in lv['A']]
+            lv['xb'] = [ops.zeros(a.ncol + a.nghost, dev) for a in lv['A']]
+            lv['d'] = [ops.zeros(a.nloc, dev) for a in lv['A']]
+            lv['r'] = [ops.zeros(r.ncol + r.nghost, dev) for r in lv['R']]          # fine residual, R's column layout
+            lv['bc'] = [ops.zeros(r.nloc, dev) for r in lv['R']]
+            lv['xc'] = [ops.zeros(p_.ncol + p_.nghost, dev) for p_ in lv['P']]      # coarse iterate, P's column layout
+            lv['rho'] = self._estimate_rho(lv)
+
+    # power iteration on D^-1 A (collective; deterministic start)
+    def _estimate_rho(self, lv):
+        torch = L.require_cuda()
+        ops, comm = self.ops, self.comm
+        A, dinv = lv['A'], lv['dinv']
+        v = lv['xa']
+        w = [ops.zeros(a.nloc, v[0].device) for a in A]
+        for a, vi in zip(A, v):                                  # same start vector as the single-GPU estimate
+            h = np.arange(a.clo, a.clo + a.ncol, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+            h ^= h >> np.uint64(29)
+            h *= np.uint64(0xBF58476D1CE4E5B9)
+            h ^= h >> np.uint64(32)
+            seed = 0.5 + (h & np.uint64(0xFFFFF)).astype(np.float64) / 1048576.0
+            vi[:a.ncol] = torch.from_numpy(seed).to(vi.device)
+        lam = 1.0
+        for it in range(20):
+            sq = [torch.sum(vi[:a.ncol] ** 2).reshape(1) for a, vi in zip(A, v)]
+            comm.allreduce_sum(sq)
+            nrm = math.sqrt(float(sq[0]))
+            if not nrm > 0:
+                break
+            if it > 0:
+                lam = nrm
+            for a, vi in zip(A, v):
+                vi[:a.ncol] /= nrm
+            comm.halo(A, v)
+            for a, vi, wi, di in zip(A, v, w, dinv):
+                ops.spmv(a, vi, wi)
+                vi[:a.ncol] = di * wi
+        sq = [torch.sum(vi[:a.ncol] ** 2).reshape(1) for a, vi in zip(A, v)]
+        comm.allreduce_sum(sq)
+        if float(sq[0]) > 0:
+            lam = math.sqrt(float(sq[0]))
+        return lam
+
+    def _smooth(self, lv, cur, alt, b, zero_start):
+        """Chebyshev(degree) on D^-1 A; returns the list of buffers holding the result (cur or alt)."""
+        ops, comm = self.ops, self.comm
+        lmax = 1.1 * lv['rho']
+        lmin = lmax / self.ratio
+        theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+        sigma = theta / delta
+        rho_k = 1.0 / sigma
+        for s in range(self.degree):
+            if s == 0:
+                c1, c2 = 0.0, 1.0 / theta
+            else:
+                rho_n = 1.0 / (2.0 * sigma - rho_k)
+                c1, c2 = rho_n * rho_k, 2.0 * rho_n / delta
+                rho_k = rho_n
+            if s == 0 and zero_start:
+                for a, x, bi, di, d in zip(lv['A'], cur, b, lv['dinv'], lv['d']):
+                    ops.smoother_first(a.nloc, bi, di, c2, x, d)
+            else:
+                comm.halo(lv['A'], cur)
+                for a, xi, xo, bi, di, d in zip(lv['A'], cur, alt, b, lv['dinv'], lv['d']):
+                    ops.smoother_step(a, xi, xo, bi, di, d, c1, c2)
+                cur, alt = alt, cur
+        return cur, alt
+
+    def _cycle(self, l, b):
+        ops, comm = self.ops, self.comm
+        if l == self.lsw:
+            full = comm.allgather(b, self.offsets[l])
+            out = []
+            for part_idx, f in enumerate(full):
+                z = self.tail.precondition(f)
+                r = self.parts[part_idx].rank
+                out.append(z[self.offsets[l][r]:self.offsets[l][r + 1]])
+            return out
+        lv = self.levels[l]
+        cur, alt = self._smooth(lv, lv['xa'], lv['xb'], b, True)
+        comm.halo(lv['A'], cur)
+        for a, x, bi, r in zip(lv['A'], cur, b, lv['r']):
+            ops.spmv_axpy(a, x, bi, -1, r)                      # r[:nloc] = b - A x   (r is laid out for R's halo)
+        comm.halo(lv['R'], lv['r'])
+        for R, r, bc in zip(lv['R'], lv['r'], lv['bc']):
+            ops.spmv(R, r, bc)
+        xc = self._cycle(l + 1, lv['bc'])
+        for P, xce, x_c in zip(lv['P'], lv['xc'], xc):
+            xce[:P.ncol] = x_c
+        comm.halo(lv['P'], lv['xc'])
+        for P, xce, x in zip(lv['P'], lv['xc'], cur):
+            ops.spmv_axpy(P, xce, x, +1, x)                     # x += P x_c (owned rows)
+        cur, alt = self._smooth(lv, cur, alt, b, False)
+        return [x[:a.nloc] for a, x in zip(lv['A'], cur)]
+
+    def apply(self, r_list):
+        """z = M^-1 r (collective)."""
+        return self._cycle(0, r_list)

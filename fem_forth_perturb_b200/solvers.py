@@ -93,7 +93,8 @@ class AMGHierarchy:
     """
     MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2}
 
-    def __init__(self, A, mode='parity', degree=2, theta=0.25, max_levels=10, max_coarse=10, reorder=None):
+    def __init__(self, A, mode='parity', degree=2, theta=0.25, max_levels=10, max_coarse=10, reorder=None,
+                 upload=True):
         torch = L.require_cuda()
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {list(self.MODES)}")
@@ -120,6 +121,10 @@ class AMGHierarchy:
                                        int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_host')
         self.levels = lib.mwx_amg_num_levels(self._host)
         self.setup_host_seconds = time.perf_counter() - t0
+        self._dev = None
+        self.upload_seconds = 0.0
+        if not upload:                      # host hierarchy only (the partitioned solver distributes it itself)
+            return
         t1 = time.perf_counter()
         # coarsest level: dense pseudo-inverse (scipy 1.4.1 pinv2 semantics) through LAPACK
         Ac = self.level_matrix(self.levels - 1, 0).toarray()

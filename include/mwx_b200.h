@@ -145,6 +145,18 @@ int mwx_gather_f64(int64_t n, const double *src, const int32_t *idx, double *dst
  * y = A x.  Replaces scipy csr_matvec inside spl.cg  ref main/example1/utils.py:157. */
 int mwx_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
              const double *values, const double *x, double *y, void *stream);   /* nnz >= 0: tiling hint, -1 unknown, <= -8: -(tile rows) from mwx_spmv_plan */
+/* y = c - A x (sign < 0) or c + A x (sign > 0); c may alias y.  Residual / prolongation of the V-cycle. */
+int mwx_spmv_axpy(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
+                  const double *x, const double *c, int32_t sign, double *y, void *stream);
+/* One polynomial-smoother step (Chebyshev / damped Jacobi): d = c1 d + c2 dinv (b - A x_in); x_out = x_in + d.
+ * mwx_smoother_first is the step from a zero iterate: d = x = c2 dinv b (no SpMV). */
+int mwx_smoother_step(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                      const double *values, const double *x_in, double *x_out, const double *b,
+                      const double *dinv, double *d, double c1, double c2, void *stream);
+int mwx_smoother_first(int64_t n, const double *b, const double *dinv, double c2, double *x, double *d,
+                       void *stream);
+/* out = M v for a dense row-major n x n M (coarsest-level pseudo-inverse). */
+int mwx_dense_gemv(int64_t n, const double *M, const double *v, double *out, void *stream);
 /* Tallest SpMV row tile whose every tile fits one TMA stage; pass -(tile_rows) as `nnz` to mwx_spmv. */
 int mwx_spmv_plan(int64_t n, const int64_t *indptr, int32_t *tile_rows_host, void *stream);
 /* diag[i] = A[i,i] (0 if absent): build_pc_diag, ref main/example1/utils.py:48-50. */

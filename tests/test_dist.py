@@ -27,6 +27,7 @@ class Part:                                     # CPU stand-in for RankSystem (s
     def __init__(self, A, offsets, rank):
         self.rank, self.lo, self.hi = rank, offsets[rank], offsets[rank + 1]
         self.nloc = self.hi - self.lo
+        self.clo, self.ncol = self.lo, self.nloc
         blk = A[self.lo:self.hi].tocsr(); blk.sort_indices()
         cols = blk.indices.astype(np.int64)
         off = (cols < self.lo) | (cols >= self.hi)
@@ -188,6 +189,36 @@ def test_partitioned_pcg_independent_of_partition_count(cuda):
     assert max(its_seen.values()) - min(its_seen.values()) <= 1
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('nparts', [1, 2, 4])
+def test_distributed_vcycle_matches_single_gpu_fast_mode(cuda, nparts):
+    """Global hierarchy applied as a collective V-cycle: same iteration count as the single-GPU fast mode."""
+    torch = cuda
+    F, D, prob, Kc = _setup(6, nparts, eps2=1e-4)
+    from fem_forth_perturb_b200.solvers import Reordering
+    ro = Reordering.for_matrix(Kc)
+    ro.perm, ro.iperm = prob.partition.perm, prob.partition.iperm          # the partition's numbering
+    Kp = ro.matrix(Kc)
+    amg = D.DistAMG(prob.parts, prob.comm, Kp, switch_rows=600)
+    assert amg.lsw >= 2                                                     # at least two distributed levels
+    rng = np.random.default_rng(4)
+    b_old = rng.standard_normal(Kc.shape[0])
+    perm = prob.partition.perm.cpu().numpy()
+    b_new = torch.from_numpy(b_old[perm]).cuda()
+    # the collective V-cycle equals the single-GPU one on the same (permuted) matrix
+    single = F.AMGHierarchy(Kp, mode='chebyshev', reorder=False)
+    z_ref = single.precondition(b_new)
+    z = torch.cat(amg.apply([b_new[p.lo:p.hi].clone() for p in prob.parts]))
+    assert float(torch.linalg.norm(z - z_ref) / torch.linalg.norm(z_ref)) < 1e-8
+    xs, its, info, _ = D.dist_pcg(prob.parts, prob.comm, [b_new[p.lo:p.hi].clone() for p in prob.parts], tol=1e-8,
+                                  precond='amg', amg=amg)
+    from fem_forth_perturb_b200.solvers import _run_pcg
+    x_ref, it_ref, info_ref, _ = _run_pcg(Kp, b_new, 1e-8, None, amg=single)
+    assert info == 0 and info_ref == 0 and abs(its - it_ref) <= 1, (its, it_ref)
+    x = torch.cat(xs)
+    assert float(torch.linalg.norm(x - x_ref) / torch.linalg.norm(x_ref)) < 1e-7
+
+
 GPU_WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["MWX_ROOT"])
@@ -213,9 +244,15 @@ x_ref, it_ref = F.solver_iter_krylov(Precondition=True, tol=1e-8).solve_with_inf
 mine = xs[0].cpu().numpy(); ref = x_ref[perm][p.lo:p.hi]
 assert info == 0 and abs(its - it_ref) <= 1, (its, it_ref)
 assert np.linalg.norm(mine - ref) <= 1e-7 * np.linalg.norm(x_ref)
-amg = [F.AMGHierarchy(p.diagonal_block(), mode="chebyshev")]
+from fem_forth_perturb_b200.solvers import Reordering, _run_pcg
+ro = Reordering.for_matrix(Kc); ro.perm, ro.iperm = prob.partition.perm, prob.partition.iperm
+Kp = ro.matrix(Kc)
+amg = D.DistAMG(prob.parts, comm, (lambda: Kp), switch_rows=600)
 xs, its_a, info, _ = D.dist_pcg(prob.parts, comm, [b_new[p.lo:p.hi].clone()], tol=1e-8, precond="amg", amg=amg)
-assert info == 0
+single = F.AMGHierarchy(Kp, mode="chebyshev", reorder=False)
+x1, it1, info1, _ = _run_pcg(Kp, b_new, 1e-8, None, amg=single)
+assert info == 0 and abs(its_a - it1) <= 1, (its_a, it1)
+assert float(torch.linalg.norm(xs[0] - x1[p.lo:p.hi]) / torch.linalg.norm(x1)) < 1e-7
 sys.stdout.write(f"RANK{dist.get_rank()}-OK its={its} ref={it_ref} amg={its_a}\n"); sys.stdout.flush()
 dist.destroy_process_group()
 '''
