@@ -20,6 +20,9 @@
 #include <limits>
 #include <numeric>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../../include/mwx_b200.h"
 
@@ -310,6 +313,16 @@ extern "C" int mwx_amg_setup_host(int64_t n, const int64_t *indptr, const int32_
     }
     *out = h;
     return 0;
+}
+
+extern "C" int mwx_set_host_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 extern "C" int mwx_amg_num_levels(const mwx_amg_host_t *h) { return h ? (int)h->levels.size() : MWX_E_BADARG; }

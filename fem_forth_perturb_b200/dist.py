@@ -499,7 +499,7 @@ class DistAMG:
     residual is all-gathered and every rank runs the remaining levels redundantly with the single-GPU V-cycle.
     Smoother = Chebyshev (fast mode); iteration counts match the single-GPU fast mode to round-off."""
 
-    def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=60000,
+    def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=500000,
                  max_levels=10, ops=None):
         torch = L.require_cuda()
         from .solvers import AMGHierarchy

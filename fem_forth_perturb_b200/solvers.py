@@ -117,6 +117,8 @@ class AMGHierarchy:
         ix = np.ascontiguousarray(A.d_indices.cpu().numpy(), dtype=np.int32)
         va = np.ascontiguousarray(A.d_data.cpu().numpy(), dtype=np.float64)
         self._host = ctypes.c_void_p()
+        import os
+        lib.mwx_set_host_threads(int(os.environ.get('MWX_HOST_THREADS', os.cpu_count() or 1)))
         L.check(lib.mwx_amg_setup_host(self.n, L.ptr(ip), L.ptr(ix), L.ptr(va), float(theta), int(max_levels),
                                        int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_host')
         self.levels = lib.mwx_amg_num_levels(self._host)

@@ -181,6 +181,8 @@ int mwx_amg_setup_host(int64_t n, const int64_t *indptr_host, const int32_t *ind
                        const double *values_host, double theta, int32_t max_levels,
                        int32_t max_coarse, mwx_amg_host_t **out);
 int mwx_amg_num_levels(const mwx_amg_host_t *h);
+/* OpenMP threads of the host setup (launchers such as torchrun pin OMP_NUM_THREADS=1); returns the setting. */
+int mwx_set_host_threads(int32_t n);
 /* which: 0 = A_l, 1 = P_l (n_l x n_{l+1}), 2 = R_l (n_{l+1} x n_l).  dims_host = {rows, cols, nnz}. */
 int mwx_amg_level_dims(const mwx_amg_host_t *h, int32_t level, int32_t which, int64_t *dims_host);
 int mwx_amg_level_copy(const mwx_amg_host_t *h, int32_t level, int32_t which, int64_t *indptr_host,
