@@ -29,9 +29,9 @@ _SIGNATURES = {
     'mwx_facet_element_count': [i64, i64, vp, vp, vp],
     'mwx_pattern_count': [i64, i64, vp, vp, vp, vp, _pi64, _pi32, vp],
     'mwx_pattern_fill': [i64, i64, vp, vp, vp, vp, vp, vp, vp],
-    'mwx_assemble_morley': [i64, i64, vp, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp],
+    'mwx_assemble_morley': [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, i32, vp, vp],
     'mwx_assemble_penalty': [i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp, vp],
-    'mwx_assemble_morley_rows': [i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp],
+    'mwx_assemble_morley_rows': [i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, vp, vp],
     'mwx_axpby': [i64, f64, vp, f64, vp, vp, vp],
     'mwx_dist_rows_count': [i64, vp, vp, vp, vp, vp, vp, vp],
     'mwx_dist_rows_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],

@@ -171,9 +171,10 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
     m = ubasis.mesh
     pat = ubasis.pattern()
     vals = out if out is not None else torch.empty(pat['nnz'], dtype=torch.float64, device=m.device)
-    L.check(lib.mwx_assemble_morley(ubasis.N, m.nt, L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(pat['r2e_ptr']),
-                                    L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']), L.ptr(pat['indptr']),
-                                    f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0), 0, L.ptr(vals), st),
+    L.check(lib.mwx_assemble_morley(ubasis.N, m.nt, L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(pat['exy']), 1,
+                                    L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']),
+                                    L.ptr(pat['indptr']), f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0), 0,
+                                    L.ptr(vals), st),
             'mwx_assemble_morley')
     return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
 

@@ -89,7 +89,8 @@ class InteriorBasis:
             slot8 = torch.empty(6 * m.nt, dtype=torch.int64, device=m.device)          # 8 bytes per (row, element)
             L.check(lib.mwx_pattern_fill(self.N, m.nt, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), L.ptr(indptr),
                                          L.ptr(indices), L.ptr(slot8), st), 'mwx_pattern_fill')
-            self._pattern = dict(r2e_ptr=r2e_ptr, r2e_idx=r2e_idx, indptr=indptr, indices=indices, slot8=slot8,
+            exy = torch.empty(8 * m.nt, dtype=torch.float64, device=m.device)       # 64-byte element records
+            self._pattern = dict(r2e_ptr=r2e_ptr, r2e_idx=r2e_idx, indptr=indptr, indices=indices, slot8=slot8, exy=exy,
                                  nnz=int(nnz.value), max_row=int(maxrow.value))
         return self._pattern
 

@@ -158,9 +158,19 @@ __device__ __forceinline__ void morley_local_row(double2 x0, double2 x1, double2
 // ROWLIST = false: tile position i is matrix row i and the output is the global CSR (values + indptr).
 // ROWLIST = true : position i is row row_ids[i]; the rows are written back to back through out_indptr
 //                  (nrows + 1 entries) - a rank of the partitioned solver assembles only the rows it owns.
+// Per-element vertex coordinates (x0,y0,x1,y1,x2,y2,-,-): one 64-byte record = two sectors per (row, element)
+// pair instead of the six scattered sectors of t[3] + pxy[3]; refreshed from (pxy, t) before every assembly.
+__global__ void k_element_coords(int64_t nt, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+                                 double2 *__restrict__ exy) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    const double2 a = __ldg(pxy + t[e]), b = __ldg(pxy + t[nt + e]), c = __ldg(pxy + t[2 * nt + e]);
+    exy[4 * e] = a; exy[4 * e + 1] = b; exy[4 * e + 2] = c; exy[4 * e + 3] = make_double2(0.0, 0.0);
+}
+
 template <bool ROWLIST>
 __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
-    int64_t nrows, int64_t nt, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+    int64_t nrows, int64_t nt, const double2 *__restrict__ exy,
     const int64_t *__restrict__ r2e_ptr, const int32_t *__restrict__ r2e_idx,
     const unsigned long long *__restrict__ slot8, const int64_t *__restrict__ indptr,
     const int32_t *__restrict__ row_ids, const int64_t *__restrict__ out_indptr,
@@ -192,8 +202,7 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
             const unsigned long long sl = __ldg(slot8 + p);
             const int64_t e = code >> 3;
             const int l = code & 7;
-            const int32_t v0 = __ldg(t + e), v1 = __ldg(t + nt + e), v2 = __ldg(t + 2 * nt + e);
-            const double2 x0 = __ldg(pxy + v0), x1 = __ldg(pxy + v1), x2 = __ldg(pxy + v2);
+            const double2 x0 = __ldg(exy + 4 * e), x1 = __ldg(exy + 4 * e + 1), x2 = __ldg(exy + 4 * e + 2);
             double row[6];
             morley_local_row(x0, x1, x2, l, ca, cb, row);
 #pragma unroll
@@ -345,31 +354,50 @@ extern "C" int mwx_pattern_fill(int64_t ndofs, int64_t nt, const int32_t *edofs,
     return 0;
 }
 
-extern "C" int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy, const int32_t *t,
-                                   const int64_t *r2e_ptr, const int32_t *r2e_idx, const uint8_t *slot8,
-                                   const int64_t *indptr, double ca, double cb, int32_t accumulate,
-                                   double *values, void *stream) {
-    if (ndofs <= 0 || nt <= 0 || !pxy || !t || !r2e_ptr || !r2e_idx || !slot8 || !indptr || !values)
+static int refresh_element_coords(int64_t nt, const double *pxy, const int32_t *t, double *exy, cudaStream_t st) {
+    k_element_coords<<<grid_for(nt, 256), 256, 0, st>>>(nt, (const double2 *)pxy, t, (double2 *)exy);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy, const int32_t *t, double *exy,
+                                   int32_t refresh_exy, const int64_t *r2e_ptr, const int32_t *r2e_idx,
+                                   const uint8_t *slot8, const int64_t *indptr, double ca, double cb,
+                                   int32_t accumulate, double *values, void *stream) {
+    if (ndofs <= 0 || nt <= 0 || !pxy || !t || !exy || !r2e_ptr || !r2e_idx || !slot8 || !indptr || !values)
         return MWX_E_BADARG;
-    if (((uintptr_t)slot8 & 7) || ((uintptr_t)pxy & 15)) return MWX_E_BADARG;
+    if (((uintptr_t)slot8 & 7) || ((uintptr_t)pxy & 15) || ((uintptr_t)exy & 63)) return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    if (refresh_exy) {
+        int rc = refresh_element_coords(nt, pxy, t, exy, st);
+        if (rc) return rc;
+    }
     const unsigned grid = (unsigned)((ndofs + ASM_ROWS - 1) / ASM_ROWS);
-    k_assemble_morley<false><<<grid, ASM_ROWS, 0, as_stream(stream)>>>(
-        ndofs, nt, (const double2 *)pxy, t, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, nullptr,
+    k_assemble_morley<false><<<grid, ASM_ROWS, 0, st>>>(
+        ndofs, nt, (const double2 *)exy, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, nullptr,
         nullptr, ca, cb, accumulate, values);
     MWX_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int mwx_assemble_morley_rows(int64_t nrows, const int32_t *row_ids, const int64_t *out_indptr,
-                                        int64_t nt, const double *pxy, const int32_t *t, const int64_t *r2e_ptr,
-                                        const int32_t *r2e_idx, const uint8_t *slot8, const int64_t *indptr,
-                                        double ca, double cb, double *values, void *stream) {
-    if (nrows < 0 || nt <= 0 || !pxy || !t || !r2e_ptr || !r2e_idx || !slot8 || !indptr || !values) return MWX_E_BADARG;
+                                        int64_t nt, const double *pxy, const int32_t *t, double *exy,
+                                        int32_t refresh_exy, const int64_t *r2e_ptr, const int32_t *r2e_idx,
+                                        const uint8_t *slot8, const int64_t *indptr, double ca, double cb,
+                                        double *values, void *stream) {
+    if (nrows < 0 || nt <= 0 || !pxy || !t || !exy || !r2e_ptr || !r2e_idx || !slot8 || !indptr || !values)
+        return MWX_E_BADARG;
     if (nrows == 0) return 0;
-    if (!row_ids || !out_indptr || ((uintptr_t)slot8 & 7) || ((uintptr_t)pxy & 15)) return MWX_E_BADARG;
+    if (!row_ids || !out_indptr || ((uintptr_t)slot8 & 7) || ((uintptr_t)pxy & 15) || ((uintptr_t)exy & 63))
+        return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    if (refresh_exy) {
+        int rc = refresh_element_coords(nt, pxy, t, exy, st);
+        if (rc) return rc;
+    }
     const unsigned grid = (unsigned)((nrows + ASM_ROWS - 1) / ASM_ROWS);
-    k_assemble_morley<true><<<grid, ASM_ROWS, 0, as_stream(stream)>>>(
-        nrows, nt, (const double2 *)pxy, t, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, row_ids,
+    k_assemble_morley<true><<<grid, ASM_ROWS, 0, st>>>(
+        nrows, nt, (const double2 *)exy, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, row_ids,
         out_indptr, ca, cb, 0, values);
     MWX_LAUNCH_CHECK();
     return 0;

@@ -167,7 +167,7 @@ class RankSystem(HaloPlan):
         f = as_form(form)
         m, pat, lib, st = self.basis.mesh, self.basis.pattern(), L.lib(), L.stream()
         L.check(lib.mwx_assemble_morley_rows(self.nloc, L.ptr(self.rows), L.ptr(self.raw_indptr), m.nt, L.ptr(m.d_pxy),
-                                             L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']),
+                                             L.ptr(m.d_t), L.ptr(pat['exy']), 1, L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']),
                                              L.ptr(pat['slot8']), L.ptr(pat['indptr']), f.terms.get('a_load', 0.0),
                                              f.terms.get('b_load', 0.0), L.ptr(self.raw_vals), st),
                 'mwx_assemble_morley_rows')

@@ -86,10 +86,13 @@ int mwx_pattern_fill(int64_t ndofs, int64_t nt, const int32_t *edofs, const int6
  * element order per CSR slot (deterministic, no atomics).  Replaces
  *   K2 = epsilon**2 * asm(a_load, basis['u']) + asm(b_load, basis['u'])   ref main/example1/run.py:210
  * (a_load/b_load: ref main/example1/run.py:110-123).  accumulate != 0 adds into values. */
-int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy, const int32_t *t,
-                        const int64_t *r2e_ptr, const int32_t *r2e_idx, const uint8_t *slot8,
-                        const int64_t *indptr, double ca, double cb, int32_t accumulate,
-                        double *values, void *stream);
+int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy, const int32_t *t, double *exy,
+                        int32_t refresh_exy, const int64_t *r2e_ptr, const int32_t *r2e_idx,
+                        const uint8_t *slot8, const int64_t *indptr, double ca, double cb,
+                        int32_t accumulate, double *values, void *stream);
+/* exy: workspace of 8*nt doubles (64-byte aligned): per-element vertex coordinates (x0,y0,x1,y1,x2,y2,-,-), one
+ * 64-byte record per element so that a (row, element) pair costs two sectors instead of six scattered ones;
+ * refresh_exy != 0 regathers it from (pxy, t) first (needed whenever the coordinates changed). */
 
 /* Boundary-facet (Nitsche penalty) terms, ref main/example1/run.py:134-146,253-260:
  * values += c1*penalty_1 + c2*penalty_2 + c3*penalty_3(sigma) over nbf boundary facets (FacetBasis:
@@ -111,9 +114,9 @@ int mwx_axpby(int64_t n, double alpha, const double *a, double beta, const doubl
  * communication): row_ids (nrows) lists matrix rows, the rows are written back to back through out_indptr
  * (nrows+1; out_indptr[i+1]-out_indptr[i] = length of row row_ids[i] in the global pattern). */
 int mwx_assemble_morley_rows(int64_t nrows, const int32_t *row_ids, const int64_t *out_indptr, int64_t nt,
-                             const double *pxy, const int32_t *t, const int64_t *r2e_ptr,
-                             const int32_t *r2e_idx, const uint8_t *slot8, const int64_t *indptr,
-                             double ca, double cb, double *values, void *stream);
+                             const double *pxy, const int32_t *t, double *exy, int32_t refresh_exy,
+                             const int64_t *r2e_ptr, const int32_t *r2e_idx, const uint8_t *slot8,
+                             const int64_t *indptr, double ca, double cb, double *values, void *stream);
 
 /* ------------------------------------------------------------------ condense (glue A -> B)
  * Replaces condense(K2, f2, D=...) ref main/example1/utils.py:384-460:
