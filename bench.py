@@ -394,7 +394,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     bf = gm.boundary_facets()
     Dset = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
     t0 = time.perf_counter()
-    comm = D.TorchDistComm()
+    # halo exchange: pack-and-push kernels into the neighbours' peer memory over NVLink (MWX_HALO=nccl: send/recv)
+    comm = D.TorchDistComm() if os.environ.get('MWX_HALO', 'peer') == 'nccl' else D.SymmMemComm()
     prob = D.PartitionedProblem(basis, Dset, comm).assemble(form)
     (p,) = prob.parts
     torch.cuda.synchronize()
@@ -403,7 +404,7 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     p.ops = ops
     n_glob = prob.partition.n
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    xs_ext = torch.zeros(p.nloc + p.nghost, dtype=torch.float64, device=dev)
+    xs_ext = comm.ext_zeros(p, dev)
     xs_ext[:p.nloc] = torch.rand(p.nloc, dtype=torch.float64, device=dev, generator=g) * 2 - 1
     comm.halo([p], [xs_ext])
     b = torch.empty(p.nloc, dtype=torch.float64, device=dev)
@@ -496,7 +497,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
                                f'condensed n={n_glob}, RCB-partitioned into {world} row blocks (Hilbert order inside a block); '
                                f'eps={EPS}, tol={TOL}, rhs=K2c@x*; preconditioner = global RS-AMG hierarchy applied as a '
                                f'collective Chebyshev V-cycle ({ml.lsw} row-blocked levels, tail of {nlev - ml.lsw} levels '
-                               f'replicated); halo exchanges + all-reduces over NCCL',
+                               f'replicated); halo = '
+                               + ('NCCL send/recv' if isinstance(comm, D.TorchDistComm) and not isinstance(comm, D.SymmMemComm) else 'pack-and-push kernels into peer memory over NVLink + signal-pad barrier') + ', all-reduces over NCCL',
                    'l2': 'per-rank operator exceeds the 126 MB L2 for level >= 11; 256 MiB written before the SpMV sample'},
         'assembly_mdof_s': N / (float(phmax[0]) * 1e-3) / 1e6, 'assembly_ms': float(phmax[0]),
         'pcg': {'s_per_solve': float(phmax[2]) * 1e-3, 'iters': iters, 'info': rs[-1]['info'], 'mode': 'distributed chebyshev V-cycle',

@@ -232,7 +232,7 @@ basis = F.InteriorBasis(gm, F.ElementTriMorley())
 bf = gm.boundary_facets()
 Dset = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
 form = 1e-4 * F.a_load + F.b_load
-comm = D.TorchDistComm()
+comm = D.SymmMemComm() if os.environ.get("MWX_TEST_HALO") == "peer" else D.TorchDistComm()
 prob = D.PartitionedProblem(basis, Dset, comm).assemble(form)
 (p,) = prob.parts
 Kc = F.condense(F.asm_gpu(form, basis), D=Dset, expand=False)
@@ -259,11 +259,13 @@ dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_partitioned_pcg_nccl_two_gpus(cuda, tmp_path):
+@pytest.mark.parametrize('halo', ['nccl', 'peer'])
+def test_partitioned_pcg_two_gpus(cuda, tmp_path, halo):
+    """halo = NCCL send/recv, or pack-and-push kernels into the neighbour's peer memory (symmetric memory)."""
     if cuda.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
     script = tmp_path / 'worker_gpu.py'
     script.write_text(GPU_WORKER)
-    res = _torchrun(str(script), 2, timeout=600)
+    res = _torchrun(str(script), 2, extra_env={'MWX_TEST_HALO': halo}, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count('-OK') == 2
