@@ -237,6 +237,31 @@ def test_properties_at_4M_dofs(cuda):
     assert torch.equal(K.d_data, K_again.d_data)
 
 
+def test_8k_mesh_needs_int64_indptr(cuda):
+    """Level 13 (8192^2 squares): 268 M DOFs, nnz = 3 087 138 817 > 2^31 - the 8k x 8k microbench config."""
+    import fem_forth_perturb_b200 as F
+    torch = cuda
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip('needs ~80 GB of free HBM')
+    gm = F.MeshTri().refine(13)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    K = F.asm_gpu(1e-4 * F.a_load + F.b_load, basis)
+    assert K.shape[0] == (2 ** 14 + 1) ** 2 == 268468225
+    assert K.nnz == 46 * 4 ** 13 + 16 * 2 ** 13 + 1 == 3087138817 and K.nnz > 2 ** 31
+    assert int(K.d_indptr[-1]) == K.nnz and K.d_indptr.dtype == torch.int64
+    one = torch.cat((torch.ones(gm.nv, dtype=torch.float64, device=gm.device),
+                     torch.zeros(gm.nf, dtype=torch.float64, device=gm.device)))
+    assert float(K.dot(one).abs().max()) < 1e-9                      # constants are in the kernel of K2
+    g = torch.Generator(device=gm.device).manual_seed(1)
+    x = torch.rand(K.shape[0], dtype=torch.float64, device=gm.device, generator=g)
+    y = torch.rand(K.shape[0], dtype=torch.float64, device=gm.device, generator=g)
+    a, b = float(torch.dot(x, K.dot(y))), float(torch.dot(y, K.dot(x)))
+    assert abs(a - b) <= 1e-12 * abs(a)
+    del K, basis, gm, x, y, one
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------ PCG (Jacobi) parity
 @pytest.mark.parametrize('level,eps', [(2, 1.0), (4, 1.0), (5, 1e-2), (6, 1e-4)])
 def test_pcg_jacobi_matches_oracle_cg(cuda, level, eps):
