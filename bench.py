@@ -225,7 +225,6 @@ def main():
     t0 = time.perf_counter()
     ml = F.AMGHierarchy(Kc, mode=args.mode)
     t_amg = time.perf_counter() - t0
-    from fem_forth_perturb_b200.solvers import _run_pcg
     # pinned host inputs / outputs for the end-to-end leg
     p_host = torch.empty(2 * gm.nv, dtype=torch.float64).pin_memory()
     t_host = torch.empty(3 * gm.nt, dtype=torch.int32).pin_memory()
@@ -272,7 +271,7 @@ def main():
         L.check(L.lib().mwx_spmv(n, ks_hint, L.ptr(Ks.d_indptr), L.ptr(Ks.d_indices), L.ptr(Ks.d_data), L.ptr(xstar),
                                  L.ptr(ysp), L.stream()), 'mwx_spmv')
         marks[6].record()
-        x, its, info, resid = _run_pcg(Kcs, bd, TOL, 2000, amg=ml)
+        x, its, info, resid = F.pcg(Kcs, bd, TOL, 2000, amg=ml)
         marks[7].record()
         if e2e:
             x_host.copy_(x, non_blocking=True)

@@ -99,8 +99,12 @@ __device__ __forceinline__ double sel3(int i, double a, double b, double c) {
 // in ascending GLOBAL order (that fixes the edge-normal orientation n_k = R(x_a - x_b)/|.|, a<b).
 //   H(psi_k) = 2 gam_k n_k n_k^T,  H(phi_i) = sum_k Dv_ik H(psi_k),  Dv_ik = -n_k . grad(lambda_i)
 //   A = |K| H:H,   B_vv = |K| (g_i.g_j - 1/3 sum_k c_ik c_jk),  B_ee = |K|/3 I,  B_ve = 0.
-__device__ __forceinline__ void morley_local_row(double2 x0, double2 x1, double2 x2, int l,
-                                                 double ca, double cb, double out[6]) {
+// The geometry of one triangle as the element kernel needs it: gam_k (3), mu_km (3), |K| - seven doubles,
+// stored with one pad double as a 64-byte record so the six (row, element) pairs of an element do the
+// rsqrt / reciprocal work once (in k_element_geometry) instead of six times.
+struct MorleyGeom { double g0, g1, g2, m01, m02, m12, area, pad; };
+
+__device__ __forceinline__ MorleyGeom morley_geometry(double2 x0, double2 x1, double2 x2) {
     // edge vectors d_k = x_a - x_b for local edges (0,1),(1,2),(0,2); t_k = R d_k = (-d.y, d.x)
     const double d0x = x0.x - x1.x, d0y = x0.y - x1.y;
     const double d1x = x1.x - x2.x, d1y = x1.y - x2.y;
@@ -116,6 +120,13 @@ __device__ __forceinline__ void morley_local_row(double2 x0, double2 x1, double2
     const double m01 = (d0x * d1x + d0y * d1y) * (r0 * r1);
     const double m02 = (d0x * d2x + d0y * d2y) * (r0 * r2);
     const double m12 = (d1x * d2x + d1y * d2y) * (r1 * r2);
+    MorleyGeom G;
+    G.g0 = g0; G.g1 = g1; G.g2 = g2; G.m01 = m01; G.m02 = m02; G.m12 = m12; G.area = area; G.pad = 0.0;
+    return G;
+}
+
+__device__ __forceinline__ void morley_local_row(const MorleyGeom &G, int l, double ca, double cb, double out[6]) {
+    const double g0 = G.g0, g1 = G.g1, g2 = G.g2, m01 = G.m01, m02 = G.m02, m12 = G.m12, area = G.area;
     // E_km = |K| (2 gam_k)(2 gam_m) mu_km^2  (edge-edge block of A)
     const double a4 = 4.0 * area;
     const double E00 = a4 * g0 * g0, E11 = a4 * g1 * g1, E22 = a4 * g2 * g2;
@@ -158,16 +169,33 @@ __device__ __forceinline__ void morley_local_row(double2 x0, double2 x1, double2
 // ROWLIST = false: tile position i is matrix row i and the output is the global CSR (values + indptr).
 // ROWLIST = true : position i is row row_ids[i]; the rows are written back to back through out_indptr
 //                  (nrows + 1 entries) - a rank of the partitioned solver assembles only the rows it owns.
-// Per-element vertex coordinates (x0,y0,x1,y1,x2,y2,-,-): one 64-byte record = two sectors per (row, element)
-// pair instead of the six scattered sectors of t[3] + pxy[3]; refreshed from (pxy, t) before every assembly.
-__global__ void k_element_coords(int64_t nt, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
-                                 double2 *__restrict__ exy) {
+// Per-element geometry record (MorleyGeom, 64 bytes = two sectors per (row, element) pair instead of the six
+// scattered sectors of t[3] + pxy[3]); recomputed from the vertex coordinates before every assembly.
+__global__ void k_element_geometry(int64_t nt, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+                                   double2 *__restrict__ exy) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nt) return;
-    const double2 a = __ldg(pxy + t[e]), b = __ldg(pxy + t[nt + e]), c = __ldg(pxy + t[2 * nt + e]);
-    exy[4 * e] = a; exy[4 * e + 1] = b; exy[4 * e + 2] = c; exy[4 * e + 3] = make_double2(0.0, 0.0);
+    const MorleyGeom G = morley_geometry(__ldg(pxy + t[e]), __ldg(pxy + t[nt + e]), __ldg(pxy + t[2 * nt + e]));
+    exy[4 * e] = make_double2(G.g0, G.g1);
+    exy[4 * e + 1] = make_double2(G.g2, G.m01);
+    exy[4 * e + 2] = make_double2(G.m02, G.m12);
+    exy[4 * e + 3] = make_double2(G.area, 0.0);
 }
 
+constexpr int ASM_MAXP = 8;               // (row, element) pairs per row staged in shared memory
+
+__device__ __forceinline__ MorleyGeom load_geom(const double2 *__restrict__ exy, int64_t e) {
+    const double2 ra = __ldg(exy + 4 * e), rb = __ldg(exy + 4 * e + 1), rc = __ldg(exy + 4 * e + 2),
+                  rd = __ldg(exy + 4 * e + 3);
+    MorleyGeom G;
+    G.g0 = ra.x; G.g1 = ra.y; G.g2 = rb.x; G.m01 = rb.y; G.m02 = rc.x; G.m12 = rc.y; G.area = rd.x; G.pad = 0.0;
+    return G;
+}
+
+// One thread owns one matrix row.  Its incidence codes and slot words (contiguous per row) are fetched in one
+// burst into shared memory; the 64-byte geometry record of pair q+1 is in flight while pair q is evaluated;
+// the six slot updates of a pair (distinct columns) are issued as six loads, six adds, six stores on the
+// shared-memory image of the row.  Rows are summed in ascending element order - no atomics, bit-reproducible.
 template <bool ROWLIST>
 __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
     int64_t nrows, int64_t nt, const double2 *__restrict__ exy,
@@ -176,6 +204,8 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
     const int32_t *__restrict__ row_ids, const int64_t *__restrict__ out_indptr,
     double ca, double cb, int accumulate, double *__restrict__ values) {
     __shared__ double acc[ASM_CAP];
+    __shared__ unsigned long long s_slot[ASM_MAXP][ASM_ROWS];
+    __shared__ int32_t s_code[ASM_MAXP][ASM_ROWS];
     const int64_t *optr = ROWLIST ? out_indptr : indptr;
     const int64_t i0 = (int64_t)blockIdx.x * ASM_ROWS;
     const int64_t i1 = i0 + ASM_ROWS < nrows ? i0 + ASM_ROWS : nrows;
@@ -183,38 +213,63 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
     const int64_t len = s1 - s0;
     const bool staged = len <= ASM_CAP;          // CTA-uniform
     const int64_t i = i0 + threadIdx.x;
+    const int tid = threadIdx.x;
 
+    int64_t pb = 0;
+    int np = 0;
+    int64_t rs = 0;
+    if (i < i1) {
+        const int64_t r = ROWLIST ? (int64_t)row_ids[i] : i;
+        pb = r2e_ptr[r];
+        np = (int)(r2e_ptr[r + 1] - pb);
+        rs = optr[i];
+#pragma unroll
+        for (int q = 0; q < ASM_MAXP; ++q)
+            if (q < np) {
+                s_code[q][tid] = __ldg(r2e_idx + pb + q);
+                s_slot[q][tid] = __ldg(slot8 + pb + q);
+            }
+    }
     if (staged) {
-        for (int k = threadIdx.x; k < (int)len; k += ASM_ROWS) acc[k] = 0.0;
+        for (int k = tid; k < (int)len; k += ASM_ROWS) acc[k] = 0.0;
         __syncthreads();
     }
     if (i < i1) {
-        const int64_t r = ROWLIST ? (int64_t)row_ids[i] : i;
-        const int64_t rs = optr[i];
-        double *dst = staged ? acc + (rs - s0) : values + rs;
         if (!staged && !accumulate) {
             const int64_t re = optr[i + 1];
             for (int64_t k = rs; k < re; ++k) values[k] = 0.0;
         }
-        const int64_t pb = r2e_ptr[r], pe = r2e_ptr[r + 1];
-        for (int64_t p = pb; p < pe; ++p) {
-            const int32_t code = __ldg(r2e_idx + p);
-            const unsigned long long sl = __ldg(slot8 + p);
-            const int64_t e = code >> 3;
-            const int l = code & 7;
-            const double2 x0 = __ldg(exy + 4 * e), x1 = __ldg(exy + 4 * e + 1), x2 = __ldg(exy + 4 * e + 2);
+        double *arow = acc + (rs - s0);
+        MorleyGeom G;
+        if (np > 0) G = load_geom(exy, (int64_t)(s_code[0][tid] >> 3));
+        for (int q = 0; q < np; ++q) {
+            const int32_t code = q < ASM_MAXP ? s_code[q][tid] : __ldg(r2e_idx + pb + q);
+            const unsigned long long sl = q < ASM_MAXP ? s_slot[q][tid] : __ldg(slot8 + pb + q);
+            const MorleyGeom Gc = G;
+            if (q + 1 < np) {                      // next pair's record is in flight during this pair's math
+                const int32_t cn = q + 1 < ASM_MAXP ? s_code[q + 1][tid] : __ldg(r2e_idx + pb + q + 1);
+                G = load_geom(exy, (int64_t)(cn >> 3));
+            }
             double row[6];
-            morley_local_row(x0, x1, x2, l, ca, cb, row);
+            morley_local_row(Gc, code & 7, ca, cb, row);
+            if (staged) {
+                double o[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) dst[(sl >> (8 * j)) & 0xffull] += row[j];
+                for (int j = 0; j < 6; ++j) o[j] = arow[(sl >> (8 * j)) & 0xffull];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) arow[(sl >> (8 * j)) & 0xffull] = o[j] + row[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) values[rs + ((sl >> (8 * j)) & 0xffull)] += row[j];
+            }
         }
     }
     if (staged) {
         __syncthreads();
         if (accumulate)
-            for (int k = threadIdx.x; k < (int)len; k += ASM_ROWS) values[s0 + k] += acc[k];
+            for (int k = tid; k < (int)len; k += ASM_ROWS) values[s0 + k] += acc[k];
         else
-            for (int k = threadIdx.x; k < (int)len; k += ASM_ROWS) values[s0 + k] = acc[k];
+            for (int k = tid; k < (int)len; k += ASM_ROWS) values[s0 + k] = acc[k];
     }
 }
 
@@ -355,7 +410,7 @@ extern "C" int mwx_pattern_fill(int64_t ndofs, int64_t nt, const int32_t *edofs,
 }
 
 static int refresh_element_coords(int64_t nt, const double *pxy, const int32_t *t, double *exy, cudaStream_t st) {
-    k_element_coords<<<grid_for(nt, 256), 256, 0, st>>>(nt, (const double2 *)pxy, t, (double2 *)exy);
+    k_element_geometry<<<grid_for(nt, 256), 256, 0, st>>>(nt, (const double2 *)pxy, t, (double2 *)exy);
     MWX_LAUNCH_CHECK();
     return 0;
 }

@@ -188,8 +188,10 @@ class AMGHierarchy:
             pass
 
 
-def _run_pcg(A, b, tol, maxiter, precondition=True, amg=None, reordering=None):
-    """Device PCG; returns (x torch, iters, info, resid)."""
+def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=None):
+    """Device PCG with scipy-1.4.1 semantics on a DeviceCSR / scipy matrix.  ``amg`` = a prebuilt
+    :class:`AMGHierarchy` (hierarchy reuse across solves: north_star's "built once as timed setup"), else Jacobi /
+    plain CG.  ``b`` numpy or device tensor.  Returns (x as a device tensor, iters, info, resid)."""
     torch = L.require_cuda()
     A = _to_device_csr(A)
     n = A.shape[0]
@@ -216,6 +218,9 @@ def _run_pcg(A, b, tol, maxiter, precondition=True, amg=None, reordering=None):
     if ro is not None:
         x = ro.backward(x)
     return x, int(iters.value), int(info.value), float(resid.value)
+
+
+_run_pcg = pcg
 
 
 def _reject_host_callables(kwargs):

@@ -90,7 +90,7 @@ int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy, const int3
                         int32_t refresh_exy, const int64_t *r2e_ptr, const int32_t *r2e_idx,
                         const uint8_t *slot8, const int64_t *indptr, double ca, double cb,
                         int32_t accumulate, double *values, void *stream);
-/* exy: workspace of 8*nt doubles (64-byte aligned): per-element vertex coordinates (x0,y0,x1,y1,x2,y2,-,-), one
+/* exy: workspace of 8*nt doubles (64-byte aligned): per-element geometry (gam_0..2, mu_01, mu_02, mu_12, |K|, -), one
  * 64-byte record per element so that a (row, element) pair costs two sectors instead of six scattered ones;
  * refresh_exy != 0 regathers it from (pxy, t) first (needed whenever the coordinates changed). */
 
