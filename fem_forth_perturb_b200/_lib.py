@@ -27,8 +27,12 @@ _SIGNATURES = {
     'mwx_mesh_refine': [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp],
     'mwx_element_dofs': [i64, i64, vp, vp, vp, vp],
     'mwx_facet_element_count': [i64, i64, vp, vp, vp],
-    'mwx_pattern_count': [i64, i64, vp, vp, vp, vp, _pi64, _pi32, vp],
-    'mwx_pattern_fill': [i64, i64, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_pattern_count': [i64, i64, i32, vp, vp, vp, vp, _pi64, _pi32, vp],
+    'mwx_pattern_fill': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_assemble_lagrange_laplace': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_load_vector': [i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_wv_action': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_morley_error_sums': [i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_assemble_morley': [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, i32, vp, vp],
     'mwx_assemble_penalty': [i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp, vp],
     'mwx_assemble_morley_rows': [i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, vp, vp],

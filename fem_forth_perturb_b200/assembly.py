@@ -123,6 +123,15 @@ class DeviceCSR:
 
     __matmul__ = dot
 
+    def eliminate_zeros(self):
+        """Drop stored entries that are exactly 0.0 (skfem calls ``K.eliminate_zeros()`` before ``tocsr()``)."""
+        torch = L.require_cuda()
+        mask = self.d_data != 0.0
+        csum = torch.zeros(self.nnz + 1, dtype=torch.int64, device=self.d_data.device)
+        csum[1:] = torch.cumsum(mask.to(torch.int64), 0)
+        return DeviceCSR(csum[self.d_indptr].contiguous(), self.d_indices[mask].contiguous(),
+                         self.d_data[mask].contiguous(), self.shape, coords=self.coords)
+
     @classmethod
     def from_scipy(cls, A, device=None):
         torch = L.require_cuda()
@@ -136,6 +145,46 @@ class DeviceCSR:
                    torch.from_numpy(A.data.astype(np.float64)).to(dev), A.shape)
 
 
+class MixedAction:
+    """``asm(wv_load, basis['w'], basis['u'])`` (ref main/example1/run.py:211) as an operator: the reference only
+    ever multiplies this (N_u x N_w) matrix by ``wh``, so it is applied element-wise instead of being stored."""
+
+    def __init__(self, wbasis, ubasis):
+        self.wbasis, self.ubasis = wbasis, ubasis
+        self.shape = (ubasis.N, wbasis.N)
+
+    def dot(self, wh):
+        torch = L.require_cuda()
+        is_np = isinstance(wh, np.ndarray)
+        m, ub, wb = self.ubasis.mesh, self.ubasis, self.wbasis
+        whd = torch.from_numpy(np.ascontiguousarray(wh, dtype=np.float64)).to(m.device) if is_np else wh
+        pat = ub.pattern()
+        out = torch.empty(ub.N, dtype=torch.float64, device=m.device)
+        L.check(L.lib().mwx_wv_action(ub.N, m.nt, wb.Nbfun, L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(wb.d_element_dofs),
+                                      L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(whd), L.ptr(out), L.stream()),
+                'mwx_wv_action')
+        return out.cpu().numpy() if is_np else out
+
+    __mul__ = dot
+    __matmul__ = dot
+
+    def tocsr(self):
+        raise NotImplementedError("the mixed (Morley x Lagrange) matrix is applied, not stored; use `A * wh`")
+
+
+def asm_load(form, basis):
+    """``asm(LinearForm, basis)``: host-sampled integrand, device integration -> numpy vector (like skfem)."""
+    torch = L.require_cuda()
+    m, pat = basis.mesh, basis.pattern()
+    fq = torch.from_numpy(form.sample(basis)).to(m.device)
+    out = torch.empty(basis.N, dtype=torch.float64, device=m.device)
+    X, W = basis.quadrature()
+    L.check(L.lib().mwx_load_vector(basis.N, m.nt, basis.Nbfun, len(W), L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy),
+                                    L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(fq), L.ptr(out),
+                                    L.stream()), 'mwx_load_vector')
+    return out.cpu().numpy()
+
+
 def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
     """Assemble ``form`` on ``ubasis`` -> :class:`DeviceCSR` (``.tocsr()`` gives scipy's matrix).
 
@@ -145,10 +194,34 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
     Facet forms are returned on the INTERIOR pattern so that ``eps**2*A + eps**2*P + B`` is a device axpby.
     """
     torch = L.require_cuda()
+    from .forms import LinearFormGPU
+    from .basis import ElementTriMorley
+    if isinstance(form, LinearFormGPU):
+        if isinstance(ubasis.elem, ElementTriMorley):
+            raise NotImplementedError("load vectors are implemented for the P1 / P2 w-problem")
+        return asm_load(form, ubasis)
     f = as_form(form)
+    if f.kind == 'mixed':
+        if vbasis is None or not isinstance(vbasis.elem, ElementTriMorley) or isinstance(ubasis.elem, ElementTriMorley):
+            raise NotImplementedError("wv_load: trial basis P1/P2, test basis Morley (ref run.py:211)")
+        return MixedAction(ubasis, vbasis)
     if vbasis is not None and vbasis is not ubasis:
-        raise NotImplementedError("asm_gpu: mixed trial/test bases are not on the device path yet")
+        raise NotImplementedError("asm_gpu: mixed trial/test bases only for wv_load")
     lib, st = L.lib(), L.stream()
+    if f.kind == 'lagrange':
+        if isinstance(ubasis.elem, ElementTriMorley):
+            raise NotImplementedError("`laplace` is the w-problem form (P1 / P2); use b_load on the Morley basis")
+        m, pat = ubasis.mesh, ubasis.pattern()
+        vals = torch.empty(pat['nnz'], dtype=torch.float64, device=m.device)
+        L.check(lib.mwx_assemble_lagrange_laplace(ubasis.N, m.nt, ubasis.Nbfun, L.ptr(m.d_pxy), L.ptr(m.d_t),
+                                                  L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']),
+                                                  L.ptr(pat['indptr']), L.ptr(vals), st), 'mwx_assemble_lagrange_laplace')
+        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
+        scale = f.terms['laplace']
+        K = K if scale == 1.0 else scale * K
+        return K.eliminate_zeros()              # skfem: COO.eliminate_zeros() -> 5-point pattern on this mesh
+    if not isinstance(ubasis, FacetBasis) and not isinstance(getattr(ubasis, 'elem', None), ElementTriMorley):
+        raise NotImplementedError("a_load / b_load are the Morley forms; use `laplace` on P1 / P2")
     if isinstance(ubasis, FacetBasis):
         if f.kind != 'facet':
             raise NotImplementedError("interior forms need an InteriorBasis")
@@ -180,3 +253,26 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
 
 
 asm = asm_gpu
+
+
+def morley_error_norms(basis, uh, exact_u, dexact_u, ddexact):
+    """(L2, D1, D2) = (||u_h - u||_0, |u_h - u|_{1,h}, |u_h - u|_{2,h}) as ref main/example1/run.py:157-179,519-531
+    (``L2uError``, ``get_DuError``, ``get_D2uError``): the exact solution is sampled at the quadrature points on
+    the host (it is a Python function), the element integrals and their sum run on the device."""
+    torch = L.require_cuda()
+    m = basis.mesh
+    x = basis.global_coordinates()
+    u = exact_u(x[0], x[1])
+    ux, uy = dexact_u(x[0], x[1])
+    uxx, uxy, _, uyy = ddexact(x[0], x[1])
+    ex = np.ascontiguousarray(np.stack([np.broadcast_to(a, x[0].shape) for a in (u, ux, uy, uxx, uxy, uyy)]),
+                              dtype=np.float64)
+    exd = torch.from_numpy(ex).to(m.device)
+    uhd = torch.from_numpy(np.ascontiguousarray(uh, dtype=np.float64)).to(m.device) if isinstance(uh, np.ndarray) else uh
+    sums = torch.empty(3, dtype=torch.float64, device=m.device)
+    _, W = basis.quadrature()
+    L.check(L.lib().mwx_morley_error_sums(m.nt, len(W), L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy), L.ptr(m.d_t),
+                                          L.ptr(basis.d_element_dofs), L.ptr(uhd), L.ptr(exd), L.ptr(sums), L.stream()),
+            'mwx_morley_error_sums')
+    s = np.sqrt(sums.cpu().numpy())
+    return float(s[0]), float(s[1]), float(s[2])

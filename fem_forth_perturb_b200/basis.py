@@ -73,26 +73,50 @@ class InteriorBasis:
     # -- CSR pattern + slot map (cached; setup cost, timed separately by bench.py) ------------------
     def pattern(self):
         if self._pattern is None:
-            if not isinstance(self.elem, ElementTriMorley):
-                raise NotImplementedError("device CSR pattern is implemented for ElementTriMorley")
             torch = L.require_cuda()
             lib, st, m = L.lib(), L.stream(), self.mesh
-            ed = self.d_element_dofs
+            ed, nb = self.d_element_dofs, self.Nbfun
             r2e_ptr = torch.empty(self.N + 1, dtype=torch.int64, device=m.device)
-            r2e_idx = torch.empty(6 * m.nt, dtype=torch.int32, device=m.device)
-            L.check(lib.mwx_incidence(self.N, m.nt, 6, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), st), 'mwx_incidence')
+            r2e_idx = torch.empty(nb * m.nt, dtype=torch.int32, device=m.device)
+            L.check(lib.mwx_incidence(self.N, m.nt, nb, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), st), 'mwx_incidence')
             indptr = torch.empty(self.N + 1, dtype=torch.int64, device=m.device)
             nnz, maxrow = ctypes.c_int64(0), ctypes.c_int32(0)
-            L.check(lib.mwx_pattern_count(self.N, m.nt, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), L.ptr(indptr),
+            L.check(lib.mwx_pattern_count(self.N, m.nt, nb, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), L.ptr(indptr),
                                           ctypes.byref(nnz), ctypes.byref(maxrow), st), 'mwx_pattern_count')
             indices = torch.empty(nnz.value, dtype=torch.int32, device=m.device)
-            slot8 = torch.empty(6 * m.nt, dtype=torch.int64, device=m.device)          # 8 bytes per (row, element)
-            L.check(lib.mwx_pattern_fill(self.N, m.nt, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), L.ptr(indptr),
+            slot8 = torch.empty(nb * m.nt, dtype=torch.int64, device=m.device)         # 8 bytes per (row, element)
+            L.check(lib.mwx_pattern_fill(self.N, m.nt, nb, L.ptr(ed), L.ptr(r2e_ptr), L.ptr(r2e_idx), L.ptr(indptr),
                                          L.ptr(indices), L.ptr(slot8), st), 'mwx_pattern_fill')
-            exy = torch.empty(8 * m.nt, dtype=torch.float64, device=m.device)       # 64-byte element records
+            # 64-byte element geometry records (Morley kernel only)
+            exy = torch.empty(8 * m.nt if isinstance(self.elem, ElementTriMorley) else 8, dtype=torch.float64,
+                              device=m.device)
             self._pattern = dict(r2e_ptr=r2e_ptr, r2e_idx=r2e_idx, indptr=indptr, indices=indices, slot8=slot8, exy=exy,
                                  nnz=int(nnz.value), max_row=int(maxrow.value))
         return self._pattern
+
+    # -- quadrature (host side: problem data - loads, exact solutions - are Python functions of these points)
+    def quadrature(self):
+        from .quadrature import triangle_rule
+        if self.intorder is None:
+            raise ValueError("this basis was built without intorder")
+        return triangle_rule(self.intorder)
+
+    def d_quadrature(self):
+        """[xi | eta | w] as one device vector (kernel argument)."""
+        if getattr(self, '_xw', None) is None:
+            torch = L.require_cuda()
+            X, W = self.quadrature()
+            self._xw = torch.from_numpy(np.concatenate((X[0], X[1], W))).to(self.mesh.device)
+        return self._xw
+
+    def global_coordinates(self):
+        """(2, nt, nq) quadrature points in global coordinates (skfem ``basis.global_coordinates().value``)."""
+        m = self.mesh
+        X, _ = self.quadrature()
+        p, t = m.p, m.t
+        x0 = p[:, t[0]]
+        return (x0[:, :, None] + (p[:, t[1]] - x0)[:, :, None] * X[0][None, None, :]
+                + (p[:, t[2]] - x0)[:, :, None] * X[1][None, None, :])
 
     def dof_coords(self):
         """Device (N, 2) fp64 DOF locations (vertices, then facet midpoints): the locality key of the

@@ -26,13 +26,13 @@ constexpr int ASM_ROWS = 128;            // rows (= threads) per CTA
 constexpr int ASM_CAP = ASM_ROWS * 24;   // shared-memory CSR slots per CTA (24 KB of fp64)
 
 // ------------------------------------------------------------------ pattern (setup)
-__device__ __forceinline__ int gather_row_cols(int64_t r, int64_t nt, const int32_t *__restrict__ edofs,
+__device__ __forceinline__ int gather_row_cols(int64_t r, int64_t nt, int ndpe, const int32_t *__restrict__ edofs,
                                                const int64_t *__restrict__ r2e_ptr,
                                                const int32_t *__restrict__ r2e_idx, int32_t *cols) {
     int n = 0;
     for (int64_t p = r2e_ptr[r]; p < r2e_ptr[r + 1]; ++p) {
         const int64_t e = r2e_idx[p] >> 3;
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < ndpe; ++j) {
             const int32_t c = edofs[(int64_t)j * nt + e];
             int pos = 0;
             while (pos < n && cols[pos] < c) ++pos;
@@ -46,7 +46,7 @@ __device__ __forceinline__ int gather_row_cols(int64_t r, int64_t nt, const int3
     return n;
 }
 
-__global__ void __launch_bounds__(128) k_pattern_count(int64_t ndofs, int64_t nt,
+__global__ void __launch_bounds__(128) k_pattern_count(int64_t ndofs, int64_t nt, int ndpe,
                                                        const int32_t *__restrict__ edofs,
                                                        const int64_t *__restrict__ r2e_ptr,
                                                        const int32_t *__restrict__ r2e_idx,
@@ -55,13 +55,13 @@ __global__ void __launch_bounds__(128) k_pattern_count(int64_t ndofs, int64_t nt
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ndofs) return;
     int32_t cols[MAX_ROW];
-    const int n = gather_row_cols(r, nt, edofs, r2e_ptr, r2e_idx, cols);
+    const int n = gather_row_cols(r, nt, ndpe, edofs, r2e_ptr, r2e_idx, cols);
     if (n < 0) { atomicExch(&stats[0], 1); row_len[r] = 0; return; }
     row_len[r] = n;
     atomicMax(&stats[1], n);
 }
 
-__global__ void __launch_bounds__(128) k_pattern_fill(int64_t ndofs, int64_t nt,
+__global__ void __launch_bounds__(128) k_pattern_fill(int64_t ndofs, int64_t nt, int ndpe,
                                                       const int32_t *__restrict__ edofs,
                                                       const int64_t *__restrict__ r2e_ptr,
                                                       const int32_t *__restrict__ r2e_idx,
@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(128) k_pattern_fill(int64_t ndofs, int64_t nt,
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ndofs) return;
     int32_t cols[MAX_ROW];
-    const int n = gather_row_cols(r, nt, edofs, r2e_ptr, r2e_idx, cols);
+    const int n = gather_row_cols(r, nt, ndpe, edofs, r2e_ptr, r2e_idx, cols);
     const int64_t s = indptr[r];
     for (int k = 0; k < n; ++k) indices[s + k] = cols[k];
     for (int64_t p = r2e_ptr[r]; p < r2e_ptr[r + 1]; ++p) {
         const int64_t e = r2e_idx[p] >> 3;
         unsigned long long w = 0;
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < ndpe; ++j) {
             const int32_t c = edofs[(int64_t)j * nt + e];
             int lo = 0, hi = n - 1;
             while (lo < hi) {
@@ -376,16 +376,17 @@ __global__ void k_axpby(int64_t n, double alpha, const double *__restrict__ a, d
 
 using namespace mwx;
 
-extern "C" int mwx_pattern_count(int64_t ndofs, int64_t nt, const int32_t *edofs, const int64_t *r2e_ptr,
+extern "C" int mwx_pattern_count(int64_t ndofs, int64_t nt, int32_t ndpe, const int32_t *edofs, const int64_t *r2e_ptr,
                                  const int32_t *r2e_idx, int64_t *indptr, int64_t *nnz_host,
                                  int32_t *max_row_host, void *stream) {
-    if (ndofs <= 0 || nt <= 0 || !edofs || !r2e_ptr || !r2e_idx || !indptr || !nnz_host) return MWX_E_BADARG;
+    if (ndofs <= 0 || nt <= 0 || ndpe < 1 || ndpe > 6 || !edofs || !r2e_ptr || !r2e_idx || !indptr || !nnz_host)
+        return MWX_E_BADARG;
     cudaStream_t st = as_stream(stream);
     Scratch<int32_t> len(st), stats(st);
     MWX_CUDA(len.alloc((size_t)ndofs));
     MWX_CUDA(stats.alloc(2));
     MWX_CUDA(cudaMemsetAsync(stats.p, 0, 2 * sizeof(int32_t), st));
-    k_pattern_count<<<grid_for(ndofs, 128), 128, 0, st>>>(ndofs, nt, edofs, r2e_ptr, r2e_idx, len.p, stats.p);
+    k_pattern_count<<<grid_for(ndofs, 128), 128, 0, st>>>(ndofs, nt, ndpe, edofs, r2e_ptr, r2e_idx, len.p, stats.p);
     MWX_LAUNCH_CHECK();
     int rc = exclusive_scan_i32_to_i64(len.p, ndofs, indptr, st);
     if (rc) return rc;
@@ -397,14 +398,15 @@ extern "C" int mwx_pattern_count(int64_t ndofs, int64_t nt, const int32_t *edofs
     return hs[0] ? MWX_E_CAPACITY : 0;
 }
 
-extern "C" int mwx_pattern_fill(int64_t ndofs, int64_t nt, const int32_t *edofs, const int64_t *r2e_ptr,
+extern "C" int mwx_pattern_fill(int64_t ndofs, int64_t nt, int32_t ndpe, const int32_t *edofs, const int64_t *r2e_ptr,
                                 const int32_t *r2e_idx, const int64_t *indptr, int32_t *indices,
                                 uint8_t *slot8, void *stream) {
     if (ndofs <= 0 || nt <= 0 || !edofs || !r2e_ptr || !r2e_idx || !indptr || !indices || !slot8)
         return MWX_E_BADARG;
     if ((uintptr_t)slot8 & 7) return MWX_E_BADARG;
+    if (ndpe < 1 || ndpe > 6) return MWX_E_BADARG;
     k_pattern_fill<<<grid_for(ndofs, 128), 128, 0, as_stream(stream)>>>(
-        ndofs, nt, edofs, r2e_ptr, r2e_idx, indptr, indices, (unsigned long long *)slot8);
+        ndofs, nt, ndpe, edofs, r2e_ptr, r2e_idx, indptr, indices, (unsigned long long *)slot8);
     MWX_LAUNCH_CHECK();
     return 0;
 }

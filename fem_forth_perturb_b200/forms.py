@@ -10,8 +10,10 @@ Descriptors form a small algebra so that ``eps**2 * a_load + b_load`` assembles 
 """
 
 INTERIOR = ('a_load', 'b_load')
+LAGRANGE = ('laplace',)          # grad.grad on P1 / P2 (w-problem)
+MIXED = ('wv_load',)             # grad(w_h) . grad(v) with w in P1/P2, v Morley (applied, not stored)
 FACET = ('penalty_1', 'penalty_2', 'penalty_3')
-KNOWN = INTERIOR + FACET
+KNOWN = INTERIOR + FACET + LAGRANGE + MIXED
 
 
 class BilinearFormGPU:
@@ -49,6 +51,10 @@ class BilinearFormGPU:
             return 'interior'
         if names <= set(FACET):
             return 'facet'
+        if names <= set(LAGRANGE):
+            return 'lagrange'
+        if names <= set(MIXED):
+            return 'mixed'
         raise NotImplementedError("interior and facet integrands need different bases; assemble them "
                                   "separately and add the matrices (as ref main/example1/run.py:260 does)")
 
@@ -61,6 +67,31 @@ b_load = BilinearFormGPU({'b_load': 1.0}, 'b_load')          # dot(grad(u), grad
 penalty_1 = BilinearFormGPU({'penalty_1': 1.0}, 'penalty_1')  # ref run.py:134-136
 penalty_2 = BilinearFormGPU({'penalty_2': 1.0}, 'penalty_2')  # ref run.py:139-141
 penalty_3 = BilinearFormGPU({'penalty_3': 1.0}, 'penalty_3')  # ref run.py:144-146 (sigma passed to asm_gpu)
+laplace = BilinearFormGPU({'laplace': 1.0}, 'laplace')        # ref run.py:149-154 (P1 / P2 bases)
+wv_load = BilinearFormGPU({'wv_load': 1.0}, 'wv_load')        # ref run.py:126-131 (trial P1/P2, test Morley)
+
+
+class LinearFormGPU:
+    """``@LinearForm def f_load(v, w): return f(w.x) * v`` (ref run.py:277-288).  The integrand is sampled on the
+    host - it is the reference's own Python closure, called with ``v = 1`` and ``w.x`` = the quadrature points -
+    and integrated against the basis on the device."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.__name__ = getattr(fn, '__name__', 'linear_form')
+
+    def sample(self, basis):
+        import numpy as np
+
+        class _W:
+            pass
+        w = _W()
+        w.x = basis.global_coordinates()
+        vals = self.fn(np.ones(w.x.shape[1:]), w)
+        return np.array(np.broadcast_to(np.asarray(vals, dtype=np.float64), w.x.shape[1:]), dtype=np.float64, order='C')
+
+
+LinearForm = LinearFormGPU
 
 
 def as_form(form):

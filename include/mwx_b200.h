@@ -72,12 +72,13 @@ int mwx_facet_element_count(int64_t nf, int64_t nt, const int32_t *t2f, int32_t 
  * Replaces scipy coo_matrix(...).tocsr() reached from skfem BilinearForm.assemble
  *   ref main/example1/run.py:210 (asm(a_load, basis['u']) + asm(b_load, basis['u'])).
  * Pass 1: row lengths -> indptr (N+1), returns nnz and the longest row. */
-int mwx_pattern_count(int64_t ndofs, int64_t nt, const int32_t *edofs, const int64_t *r2e_ptr,
+int mwx_pattern_count(int64_t ndofs, int64_t nt, int32_t ndpe, const int32_t *edofs, const int64_t *r2e_ptr,
                       const int32_t *r2e_idx, int64_t *indptr, int64_t *nnz_host,
                       int32_t *max_row_host, void *stream);
 /* Pass 2: indices (nnz, ascending per row) and the slot map: for pair p of r2e_idx (row r, element e)
- * slot8[8*p + j] = position of column edofs[j][e] inside row r (j = 0..5; bytes 6,7 unused). */
-int mwx_pattern_fill(int64_t ndofs, int64_t nt, const int32_t *edofs, const int64_t *r2e_ptr,
+ * slot8[8*p + j] = position of column edofs[j][e] inside row r (j < ndpe; other bytes unused).
+ * ndpe = DOFs per element: 6 (Morley, P2) or 3 (P1). */
+int mwx_pattern_fill(int64_t ndofs, int64_t nt, int32_t ndpe, const int32_t *edofs, const int64_t *r2e_ptr,
                      const int32_t *r2e_idx, const int64_t *indptr, int32_t *indices,
                      uint8_t *slot8, void *stream);
 
@@ -224,6 +225,27 @@ int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_
                 const double *values, const double *b, double *x, double tol, int64_t maxiter,
                 double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
                 void *stream);
+
+/* ------------------------------------------------------------------ callers either side of the hot path
+ * K1 = asm(laplace, basis['w']) for P1 (ndpe 3) / P2 (ndpe 6), ref main/example1/run.py:149-154,198 (closed form). */
+int mwx_assemble_lagrange_laplace(int64_t nrows, int64_t nt, int32_t ndpe, const double *pxy, const int32_t *t,
+                                  const int64_t *r2e_ptr, const int32_t *r2e_idx, const uint8_t *slot8,
+                                  const int64_t *indptr, double *values, void *stream);
+/* f1 = asm(f_load, basis['w']), ref run.py:277-288,199: fq (nt*nq) = the load sampled at the quadrature points
+ * (evaluated by the caller: problem data stays host Python); xw = [xi (nq) | eta (nq) | weights (nq)]. */
+int mwx_load_vector(int64_t nrows, int64_t nt, int32_t ndpe, int32_t nq, const double *xw, const double *pxy,
+                    const int32_t *t, const int64_t *r2e_ptr, const int32_t *r2e_idx, const double *fq,
+                    double *out, void *stream);
+/* f2 = asm(wv_load, basis['w'], basis['u']) * wh, ref run.py:126-131,211, applied without storing the rectangular
+ * matrix: out[r] = sum_K int grad(w_h) . grad(phi_r) over the Morley rows (r2e = Morley incidence). */
+int mwx_wv_action(int64_t nrows, int64_t nt, int32_t ndpe_w, const double *pxy, const int32_t *t,
+                  const int32_t *wdofs, const int64_t *r2e_ptr, const int32_t *r2e_idx, const double *wh,
+                  double *out, void *stream);
+/* L2uError / get_DuError / get_D2uError, ref run.py:157-179: sums3 = {int (u_h-u)^2, int |grad(u_h-u)|^2,
+ * int |hess(u_h-u)|_F^2} of a Morley function; exact6 = u, ux, uy, uxx, uxy, uyy sampled at the quadrature points. */
+int mwx_morley_error_sums(int64_t nt, int32_t nq, const double *xw, const double *pxy, const int32_t *t,
+                          const int32_t *edofs, const double *uh, const double *exact6, double *sums3,
+                          void *stream);
 
 /* ------------------------------------------------------------------ partitioned solve (no reference counterpart)
  * A rank owns the contiguous range [lo, hi) of the solver numbering.  gid (ndofs) maps a skfem DOF to its

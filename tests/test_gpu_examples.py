@@ -1,0 +1,86 @@
+"""SURVEY 8(f) rows 1-2 on the device, and the reference's example-1 tables end to end through the product path
+(no oracle inside the run; the oracle and the reference's golden CSVs are only the checkers)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle.skfem_mesh import MeshTri as OMesh
+from oracle.skfem_basis import InteriorBasis as OInterior
+from oracle import skfem_asm as oa
+from oracle import pipeline as pl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('kind', ['P1', 'P2'])
+@pytest.mark.parametrize('level', [1, 3, 4])
+def test_w_path_matches_oracle(cuda, kind, level):
+    import fem_forth_perturb_b200 as F
+    om = OMesh().refine(level)
+    gm = F.MeshTri().refine(level)
+    elem = F.ElementTriP1() if kind == 'P1' else F.ElementTriP2()
+    wb_o = OInterior(om, kind, 5)
+    wb = F.InteriorBasis(gm, elem, intorder=5)
+    # K1 = asm(laplace): same pattern after eliminate_zeros (5-point stencil for P1), values to round-off
+    K1_o = oa.asm_bilinear(oa.laplace, wb_o)
+    K1 = F.asm_gpu(F.laplace, wb).tocsr()
+    if kind == 'P1':
+        assert np.array_equal(K1.indptr, K1_o.indptr) and np.array_equal(K1.indices, K1_o.indices)
+    else:
+        # P2: entries that are mathematically zero come out of skfem's quadrature as ~1e-17 noise and stay in its
+        # pattern ("round-off luck"); the closed form gives exact zeros, which eliminate_zeros drops.
+        pat, ref = K1.copy(), K1_o.copy()
+        pat.data[:] = 1.0; ref.data[:] = 1.0
+        assert (pat - pat.multiply(ref)).nnz == 0                 # our pattern is a subset of the reference's
+    assert abs(K1 - K1_o).max() <= 1e-12 * abs(K1_o).max()
+    # f1 = asm(f_load)
+    prob = pl.Ex1(0.1)
+    f1_o = oa.asm_linear(prob.f, wb_o)
+
+    @F.LinearForm
+    def f_load(v, w):
+        return prob.f(w.x[0], w.x[1]) * v
+    f1 = F.asm_gpu(f_load, wb)
+    assert np.max(np.abs(f1 - f1_o)) <= 1e-12 * np.max(np.abs(f1_o))
+    # f2 = asm(wv_load, w, u) * wh
+    ub_o = OInterior(om, 'Morley', 5, shift=True)
+    ub = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+    wh = np.random.default_rng(0).standard_normal(wb.N)
+    f2_o = oa.asm_bilinear(oa.wv_load, wb_o, ub_o) @ wh
+    f2 = F.asm_gpu(F.wv_load, wb, ub) * wh
+    assert np.max(np.abs(f2 - f2_o)) <= 1e-11 * np.max(np.abs(f2_o))
+    # error functionals of a random Morley function
+    uh = np.random.default_rng(1).standard_normal(ub.N)
+    ex = pl.Ex1(1.0)
+    L2, D1, D2 = F.morley_error_norms(ub, uh, ex.u, ex.du, ex.ddu)
+    ub_o5 = OInterior(om, 'Morley', 5, shift=True)
+    r = pl.error_norms(uh, ub_o5, ex)
+    assert abs(L2 - r[0]) <= 1e-11 * r[0] and abs(L2 + D1 - r[1]) <= 1e-11 * r[1]
+    assert abs(L2 + D1 + D2 - r[2]) <= 1e-11 * r[2]
+
+
+@pytest.mark.parametrize('element,key', [('P1', 'ex1_P1_nopen'), ('P2', 'ex1_P2_nopen')])
+def test_example1_tables_match_reference_logs(cuda, golden_norms, golden_iterations, element, key):
+    """examples/example1.py = main/example1/run.py on the device: printed numbers agree with the reference's log
+    to 3 significant digits (north_star), in fact to the CG tolerance; iteration counts within +-1 (P1 config)."""
+    sys.path.insert(0, os.path.join(ROOT, 'examples'))
+    import example1
+    lines = []
+    results, its = example1.run(refine_time=6, epsilon_range=3, element_type=element, out=lambda *a: lines.append(a))
+    g = golden_norms[key]
+    for eps, tab in results.items():
+        gold = np.array(g['rows'][repr(float(eps))])
+        rel = np.abs(tab - gold) / np.abs(gold)
+        assert rel.max() < 5e-4, (eps, rel.max())                 # 3 significant digits
+        assert rel[0].max() < 1e-11                               # level 1 is exact after one CG step
+        for a, b in zip(tab[1:].ravel(), gold[1:].ravel()):
+            assert '{:.3e}'.format(a)[:4] == '{:.3e}'.format(b)[:4] or abs(a - b) <= 6e-4 * abs(b)
+    if element == 'P1':                                           # the golden iteration log is the P1 configuration
+        for eps, pairs in its.items():
+            gw, gu = golden_iterations['w'][repr(float(eps))][:6], golden_iterations['u'][repr(float(eps))][:6]
+            assert all(abs(p[0] - a) <= 1 for p, a in zip(pairs, gw)), (eps, pairs, gw)
+            assert all(abs(p[1] - a) <= (1 if eps != 0.1 else 2) for p, a in zip(pairs, gu)), (eps, pairs, gu)
+    assert any('epsilon = 1' in ' '.join(map(str, l)) for l in lines)
