@@ -24,6 +24,25 @@ from fem_forth_perturb_b200 import (MeshTri, ElementTriMorley, ElementTriP1, Ele
 pi, sin, cos = np.pi, np.sin, np.cos
 
 
+def make_problem_ex3(epsilon):
+    """'ex3' of ref main/example1/run.py:466-493 (used with penalty=True)."""
+    @LinearForm
+    def f_load(v, w):
+        return (2 * pi ** 2 * sin(pi * w.x[0]) * sin(pi * w.x[1])) * v
+
+    def exact_u(x, y):
+        return sin(pi * x) * sin(pi * y)
+
+    def dexact_u(x, y):
+        return pi * cos(pi * x) * sin(pi * y), pi * cos(pi * y) * sin(pi * x)
+
+    def ddexact(x, y):
+        duxx = -pi ** 2 * sin(pi * x) * sin(pi * y)
+        duxy = pi * cos(pi * x) * pi * cos(pi * y)
+        return duxx, duxy, duxy, duxx
+    return f_load, exact_u, dexact_u, ddexact
+
+
 def make_problem(epsilon):
     """'ex1' of ref main/example1/run.py:275-309."""
     @LinearForm
@@ -56,6 +75,57 @@ def easy_boundary(m, basis):
         'buttom': m.facets_satisfying(lambda x: x[1] == 0, boundaries_only=True)})
     return np.concatenate([dofs[k].nodal['u'] for k in ('left', 'right', 'top', 'buttom')]
                           + [dofs[k].facet['u_n'] for k in ('left', 'right', 'top', 'buttom')])
+
+
+def easy_boundary_penalty(m, basis):
+    """ref main/example1/run.py:67-83: nodal DOFs only - the normal derivative is imposed weakly."""
+    dofs = basis.find_dofs({
+        'left': m.facets_satisfying(lambda x: x[0] == 0, boundaries_only=True),
+        'right': m.facets_satisfying(lambda x: x[0] == 1, boundaries_only=True),
+        'top': m.facets_satisfying(lambda x: x[1] == 1, boundaries_only=True),
+        'buttom': m.facets_satisfying(lambda x: x[1] == 0, boundaries_only=True)})
+    return np.concatenate([dofs[k].nodal['u'] for k in ('left', 'right', 'top', 'buttom')])
+
+
+def solve_problem2(m, epsilon, f_load, element_type='P1', intorder=6, tol=1e-8, sigma=5, mode='parity', iters=None):
+    """ref main/example1/run.py:225-272 (penalty): K2 = eps^2 A + eps^2 P + B, nodal-only Dirichlet set."""
+    element = {'w': ElementTriP1() if element_type == 'P1' else ElementTriP2(), 'u': ElementTriMorley()}
+    basis = {v: InteriorBasis(m, e, intorder=intorder) for v, e in element.items()}
+    K1 = asm(laplace, basis['w'])
+    f1 = asm(f_load, basis['w'])
+    sw = solver_iter_mgcg(tol=tol, mode=mode)
+    wh = solve(*condense(K1, f1, D=basis['w'].find_dofs()), solver=sw)
+    fbasis = F.FacetBasis(m, element['u'])
+    fbasis.interior = basis['u']                                   # one CSR pattern for A, B and P
+    P = asm(F.penalty_1 + F.penalty_2 + F.penalty_3, fbasis, sigma=sigma)
+    K2 = asm(epsilon ** 2 * a_load + b_load, basis['u']) + epsilon ** 2 * P          # run.py:260
+    f2 = asm(wv_load, basis['w'], basis['u']) * wh
+    su = solver_iter_mgcg(tol=tol, mode=mode)
+    uh0 = solve(*condense(K2, f2, D=easy_boundary_penalty(m, basis['u'])), solver=su)
+    if iters is not None:
+        iters.append((sw.last['iters'], su.last['iters']))
+    return uh0, basis, fbasis
+
+
+def run_penalty(refine_time=7, epsilons=(1, 1e-2, 1e-4, 1e-6), element_type='P1', intorder=6, tol=1e-8, sigma=5,
+                mode='parity', out=print):
+    """The reference's 'ex3 + penalty' runs (log/ex3_range_2/ex3_P*_pen_*.csv)."""
+    results = {}
+    for epsilon in epsilons:
+        f_load, exact_u, dexact_u, ddexact = make_problem_ex3(epsilon)
+        m = MeshTri()
+        rows = []
+        for i in range(1, refine_time + 1):
+            m.refine()
+            uh0, basis, fbasis = solve_problem2(m, epsilon, f_load, element_type, intorder, tol, sigma, mode)
+            L2u, Du, D2i = morley_error_norms(basis['u'], uh0, exact_u, dexact_u, ddexact)
+            D2u = np.sqrt(D2i ** 2 + F.morley_facet_pnv(fbasis, uh0))             # run.py:527
+            rows.append((L2u, L2u + Du, L2u + Du + D2u, np.sqrt(epsilon ** 2 * D2u ** 2 + Du ** 2)))
+        results[epsilon] = np.array(rows)
+        out('epsilon =', epsilon)
+        for r in rows:
+            out(' {:.3e}  {:.3e}  {:.3e}  {:.3e}'.format(*r))
+    return results
 
 
 def solve_problem1(m, epsilon, f_load, element_type='P1', solver_type='mgcg', intorder=5, tol=1e-8, mode='parity',

@@ -276,3 +276,16 @@ def morley_error_norms(basis, uh, exact_u, dexact_u, ddexact):
             'mwx_morley_error_sums')
     s = np.sqrt(sums.cpu().numpy())
     return float(s[0]), float(s[1]), float(s[2])
+
+
+def morley_facet_pnv(fbasis, uh):
+    """``L2pnvError.assemble(fbasis, w=fbasis.interpolate(uh0))`` (ref main/example1/run.py:106-108,527):
+    sum over the boundary facets of int_F (h_F n . grad u_h)^2."""
+    torch = L.require_cuda()
+    m, ib, pl = fbasis.mesh, fbasis.interior, fbasis.plan()
+    uhd = torch.from_numpy(np.ascontiguousarray(uh, dtype=np.float64)).to(m.device) if isinstance(uh, np.ndarray) else uh
+    terms = torch.empty(pl['nbf'], dtype=torch.float64, device=m.device)
+    L.check(L.lib().mwx_morley_facet_pnv(m.nt, pl['nbf'], L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(ib.d_element_dofs),
+                                         L.ptr(pl['btri']), L.ptr(pl['blocal']), L.ptr(uhd), L.ptr(terms), L.stream()),
+            'mwx_morley_facet_pnv')
+    return float(np.sum(terms.cpu().numpy()))          # O(sqrt N) terms, summed in index order

@@ -364,6 +364,33 @@ __global__ void k_assemble_penalty(int64_t nt, const double2 *__restrict__ pxy, 
     }
 }
 
+// L2pnvError (ref main/example1/run.py:106-108,527): sum over boundary facets of int_F (h_F n . grad u_h)^2.
+// One thread per boundary facet writes its own term; the (tiny) sum is folded in index order.
+__global__ void k_facet_pnv(int64_t nt, int64_t nbf, const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+                            const int32_t *__restrict__ edofs, const int32_t *__restrict__ btri,
+                            const int32_t *__restrict__ blocal, const double *__restrict__ uh,
+                            double *__restrict__ terms) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbf) return;
+    const int64_t e = btri[b];
+    double acc = 0.0;
+    // n . grad u_h = sum_i u_i gn_i; gn_i is linear along the facet: reuse the penalty row machinery with
+    // c3 = 1, sigma = h (so that the weight is gn_i gn_j |F| w_q): sum_ij u_i u_j P3_ij = int (n.grad u_h)^2
+    const double2 x0 = pxy[t[e]], x1 = pxy[t[nt + e]], x2 = pxy[t[2 * nt + e]];
+    const int m = blocal[b];
+    double u[6];
+    for (int j = 0; j < 6; ++j) u[j] = uh[edofs[(int64_t)j * nt + e]];
+    const double dx = (m == 0 ? x0.x - x1.x : (m == 1 ? x1.x - x2.x : x0.x - x2.x));
+    const double dy = (m == 0 ? x0.y - x1.y : (m == 1 ? x1.y - x2.y : x0.y - x2.y));
+    const double h = sqrt(dx * dx + dy * dy);
+    for (int i = 0; i < 6; ++i) {
+        double row[6];
+        penalty_local_row(x0, x1, x2, m, i, 0.0, 0.0, 1.0, h, row);      // (sigma / h) = 1
+        for (int j = 0; j < 6; ++j) acc += u[i] * row[j] * u[j];
+    }
+    terms[b] = h * h * acc;
+}
+
 __global__ void k_axpby(int64_t n, double alpha, const double *__restrict__ a, double beta,
                         const double *__restrict__ b, double *__restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -493,4 +520,14 @@ extern "C" int mwx_assemble_penalty(int64_t nt, int64_t nbf, const double *pxy, 
     MWX_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MWX_CUDA(cudaStreamSynchronize(st));
     return herr ? MWX_E_BADARG : 0;
+}
+
+extern "C" int mwx_morley_facet_pnv(int64_t nt, int64_t nbf, const double *pxy, const int32_t *t, const int32_t *edofs,
+                                    const int32_t *btri, const int32_t *blocal, const double *uh, double *terms,
+                                    void *stream) {
+    if (nt <= 0 || nbf <= 0 || !pxy || !t || !edofs || !btri || !blocal || !uh || !terms) return MWX_E_BADARG;
+    k_facet_pnv<<<grid_for(nbf, 64), 64, 0, as_stream(stream)>>>(nt, nbf, (const double2 *)pxy, t, edofs, btri, blocal, uh,
+                                                                 terms);
+    MWX_LAUNCH_CHECK();
+    return 0;
 }

@@ -323,6 +323,47 @@ def solver_iter_mgcg_iter(krylov=None, verbose=False, mode='parity', degree=2, *
     return _make_mgcg(True, krylov, verbose, mode, degree, **kwargs)
 
 
+def solver_iter_pyamg(verbose=False, mode='parity', **kwargs):
+    """ref utils.py:168-210: stand-alone AMG iteration ``ml.solve(b, tol=1e-10, maxiter=10000)``.
+    A V-cycle with initial guess x equals x + M(b - A x) with M the cycle from zero, so the iteration is
+    r = b - A x;  x += V(r);  stop when ||r|| / ||b|| < tol (pyamg's test, after each cycle)."""
+    def run(A, b, **solve_time_kwargs):
+        torch = L.require_cuda()
+        kwargs.update(solve_time_kwargs)
+        A_d = _to_device_csr(A)
+        dev = A_d.d_data.device
+        ml = AMGHierarchy(A_d, mode=mode)
+        Ap = ml.reordering.matrix(A_d) if ml.reordering is not None else A_d
+        bd = _to_device_vec(b, dev)
+        if ml.reordering is not None:
+            bd = ml.reordering.forward(bd)
+        x = torch.zeros_like(bd)
+        normb = float(torch.linalg.norm(bd)) or 1.0
+        it, resid = 0, normb
+        while it < 10000:
+            r = bd - Ap.dot(x)
+            x = x + ml.precondition(r)
+            it += 1
+            resid = float(torch.linalg.norm(bd - Ap.dot(x)))
+            if verbose:
+                print(float(torch.linalg.norm(x)))
+            if resid / normb < 1e-10:
+                break
+        if ml.reordering is not None:
+            x = ml.reordering.backward(x)
+        solver.last = dict(iters=it, resid=resid)
+        if resid > 1 and verbose:
+            print('Warning: residual norm =', resid)
+        return (x.cpu().numpy() if isinstance(b, np.ndarray) else x), it
+
+    def solver(A, b, **kw):
+        return run(A, b, **kw)[0]
+
+    solver.solve_with_info = run
+    solver.last = None
+    return solver
+
+
 # ------------------------------------------------------------------ solve / condense
 def solve(A, b, x=None, I=None, solver=None, **kwargs):
     """ref utils.py:326-368 (linear systems only)."""

@@ -247,6 +247,11 @@ int mwx_morley_error_sums(int64_t nt, int32_t nq, const double *xw, const double
                           const int32_t *edofs, const double *uh, const double *exact6, double *sums3,
                           void *stream);
 
+/* L2pnvError, ref run.py:106-108,527: terms[b] = int_F (h_F n . grad u_h)^2 for each listed boundary facet. */
+int mwx_morley_facet_pnv(int64_t nt, int64_t nbf, const double *pxy, const int32_t *t, const int32_t *edofs,
+                         const int32_t *btri, const int32_t *blocal, const double *uh, double *terms,
+                         void *stream);
+
 /* ------------------------------------------------------------------ partitioned solve (no reference counterpart)
  * A rank owns the contiguous range [lo, hi) of the solver numbering.  gid (ndofs) maps a skfem DOF to its
  * solver id, or -1 for an eliminated (Dirichlet) DOF.  rows (nloc) = skfem ids of the owned DOFs in solver order.

@@ -84,3 +84,16 @@ def test_example1_tables_match_reference_logs(cuda, golden_norms, golden_iterati
             assert all(abs(p[0] - a) <= 1 for p, a in zip(pairs, gw)), (eps, pairs, gw)
             assert all(abs(p[1] - a) <= (1 if eps != 0.1 else 2) for p, a in zip(pairs, gu)), (eps, pairs, gu)
     assert any('epsilon = 1' in ' '.join(map(str, l)) for l in lines)
+
+
+def test_penalty_example_tables_match_reference_logs(cuda, golden_norms):
+    """solve_problem2 (Nitsche penalty, nodal-only BCs, L2pnvError) on the device vs log/ex3_range_2/ex3_P1_pen."""
+    sys.path.insert(0, os.path.join(ROOT, 'examples'))
+    import example1
+    results = example1.run_penalty(refine_time=5, epsilons=(1, 1e-2, 1e-4), element_type='P1', out=lambda *a: None)
+    g = golden_norms['ex3_P1_pen']
+    for eps, tab in results.items():
+        gold = np.array(g['rows'][repr(float(eps))][:5])
+        rel = np.abs(tab - gold) / np.abs(gold)
+        assert rel.max() < 5e-4, (eps, rel)
+        assert rel[0].max() < 1e-7                                # level 1: 17 unknowns, CG tolerance 1e-8

@@ -389,6 +389,20 @@ def test_locality_reordering_is_a_similarity_transform(cuda):
         F.AMGHierarchy(Kc, mode='parity', reorder=True)
 
 
+def test_solver_iter_pyamg_standalone_vcycles(cuda):
+    """solver_type='amg' (ref utils.py:168-210): same number of V-cycles as the pyamg restatement's ml.solve."""
+    import fem_forth_perturb_b200 as F
+    om = OMesh().refine(4)
+    S = pl.solve_problem(om, pl.Ex1(1e-2), wkind='P1', intorder=5, return_system=True)
+    Kc, bc = S['Kc'], S['bc']
+    Kc.sort_indices()
+    x_o, it_o = RugeStuben(Kc).solve(bc, tol=1e-10, maxiter=10000)
+    solver = F.solver_iter_pyamg()
+    x, it = solver.solve_with_info(Kc, bc)
+    assert abs(it - it_o) <= 1, (it, it_o)
+    assert np.linalg.norm(x - x_o) <= 1e-8 * np.linalg.norm(x_o)
+
+
 def test_mgcg_iter_prints_like_the_reference(cuda, capsys):
     import fem_forth_perturb_b200 as F
     om = OMesh().refine(2)
