@@ -11,15 +11,15 @@ from .mesh import MeshTri                                                # noqa:
 from .basis import (ElementTriMorley, ElementTriP1, ElementTriP2,        # noqa: F401
                     InteriorBasis, FacetBasis)
 from .forms import (BilinearFormGPU, a_load, b_load, penalty_1,          # noqa: F401
-                    penalty_2, penalty_3, laplace, wv_load, LinearForm, LinearFormGPU, as_form)
+                    penalty_2, penalty_3, laplace, wv_load, mass, LinearForm, LinearFormGPU, as_form)
 from .assembly import (asm_gpu, asm, DeviceCSR, MixedAction, morley_error_norms,   # noqa: F401
-                       morley_facet_pnv)
+                       morley_facet_pnv, project)
 from .solvers import (solver_iter_krylov, solver_iter_krylov_iter,       # noqa: F401
                       solver_iter_pcg, solver_iter_mgcg, solver_iter_mgcg_iter, solver_iter_pyamg,
                       build_pc_diag, solve, condense, CondensePlan, AMGHierarchy, pcg)
 
 __all__ = ['MeshTri', 'ElementTriMorley', 'ElementTriP1', 'ElementTriP2', 'InteriorBasis', 'FacetBasis',
            'a_load', 'b_load', 'penalty_1', 'penalty_2', 'penalty_3', 'laplace', 'wv_load', 'LinearForm', 'asm_gpu', 'asm',
-           'DeviceCSR', 'MixedAction', 'morley_error_norms', 'morley_facet_pnv',
+           'DeviceCSR', 'MixedAction', 'morley_error_norms', 'morley_facet_pnv', 'project', 'mass',
            'solver_iter_krylov', 'solver_iter_krylov_iter', 'solver_iter_pcg', 'solver_iter_mgcg',
            'solver_iter_mgcg_iter', 'solver_iter_pyamg', 'build_pc_diag', 'solve', 'condense', 'CondensePlan', 'AMGHierarchy', 'pcg', 'MwxError']

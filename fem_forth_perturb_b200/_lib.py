@@ -33,6 +33,8 @@ _SIGNATURES = {
     'mwx_load_vector': [i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_wv_action': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_morley_error_sums': [i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_assemble_morley_mass': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_morley_load_vector': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_morley_facet_pnv': [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_assemble_morley': [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, i32, vp, vp],
     'mwx_assemble_penalty': [i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp, vp],

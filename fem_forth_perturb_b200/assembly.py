@@ -179,9 +179,15 @@ def asm_load(form, basis):
     fq = torch.from_numpy(form.sample(basis)).to(m.device)
     out = torch.empty(basis.N, dtype=torch.float64, device=m.device)
     X, W = basis.quadrature()
-    L.check(L.lib().mwx_load_vector(basis.N, m.nt, basis.Nbfun, len(W), L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy),
-                                    L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(fq), L.ptr(out),
-                                    L.stream()), 'mwx_load_vector')
+    from .basis import ElementTriMorley
+    if isinstance(basis.elem, ElementTriMorley):
+        L.check(L.lib().mwx_morley_load_vector(basis.N, m.nt, len(W), L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy),
+                                               L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(fq),
+                                               L.ptr(out), L.stream()), 'mwx_morley_load_vector')
+    else:
+        L.check(L.lib().mwx_load_vector(basis.N, m.nt, basis.Nbfun, len(W), L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy),
+                                        L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(fq), L.ptr(out),
+                                        L.stream()), 'mwx_load_vector')
     return out.cpu().numpy()
 
 
@@ -197,8 +203,6 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
     from .forms import LinearFormGPU
     from .basis import ElementTriMorley
     if isinstance(form, LinearFormGPU):
-        if isinstance(ubasis.elem, ElementTriMorley):
-            raise NotImplementedError("load vectors are implemented for the P1 / P2 w-problem")
         return asm_load(form, ubasis)
     f = as_form(form)
     if f.kind == 'mixed':
@@ -208,6 +212,18 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
     if vbasis is not None and vbasis is not ubasis:
         raise NotImplementedError("asm_gpu: mixed trial/test bases only for wv_load")
     lib, st = L.lib(), L.stream()
+    if f.kind == 'mass':
+        if not isinstance(ubasis.elem, ElementTriMorley):
+            raise NotImplementedError("`mass` is implemented on the Morley basis (example 3's L2 projection)")
+        m, pat = ubasis.mesh, ubasis.pattern()
+        vals = torch.empty(pat['nnz'], dtype=torch.float64, device=m.device)
+        _, W = ubasis.quadrature()
+        L.check(lib.mwx_assemble_morley_mass(ubasis.N, m.nt, len(W), L.ptr(ubasis.d_quadrature()), L.ptr(m.d_pxy),
+                                             L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']),
+                                             L.ptr(pat['slot8']), L.ptr(pat['indptr']), L.ptr(vals), st),
+                'mwx_assemble_morley_mass')
+        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
+        return K if f.terms['mass'] == 1.0 else f.terms['mass'] * K
     if f.kind == 'lagrange':
         if isinstance(ubasis.elem, ElementTriMorley):
             raise NotImplementedError("`laplace` is the w-problem form (P1 / P2); use b_load on the Morley basis")
@@ -289,3 +305,15 @@ def morley_facet_pnv(fbasis, uh):
                                          L.ptr(pl['btri']), L.ptr(pl['blocal']), L.ptr(uhd), L.ptr(terms), L.stream()),
             'mwx_morley_facet_pnv')
     return float(np.sum(terms.cpu().numpy()))          # O(sqrt N) terms, summed in index order
+
+
+def project(fun, basis_to):
+    """``project(exact_u, basis_to=basis['u'])`` (ref main/example3/run.py:66; main/example3/utils.py:494-565):
+    global L2 projection M x = int fun phi.  The reference calls a sparse direct solver; the Morley mass matrix is
+    well conditioned, so Jacobi-PCG to 1e-14 on the device gives the same vector to round-off."""
+    from .forms import LinearFormGPU, mass
+    from .solvers import pcg
+    M = asm_gpu(mass, basis_to)
+    f = asm_gpu(LinearFormGPU(lambda v, w: fun(w.x[0], w.x[1]) * v), basis_to)
+    x, its, info, resid = pcg(M, f, tol=1e-14, maxiter=20000, precondition=True)
+    return x.cpu().numpy()

@@ -268,6 +268,59 @@ __global__ void __launch_bounds__(128) k_morley_errors(int64_t nt, int nq, const
     }
 }
 
+// Morley mass matrix rows (project(exact_u, basis_to=basis['u']), ref main/example3/run.py:66 +
+// main/example3/utils.py:494-565): quartic integrand, integrated with the basis' quadrature rule.
+__global__ void __launch_bounds__(128) k_morley_mass(int64_t nrows, int64_t nt, int nq, const double *__restrict__ XW,
+                                                     const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+                                                     const int64_t *__restrict__ r2e_ptr,
+                                                     const int32_t *__restrict__ r2e_idx,
+                                                     const unsigned long long *__restrict__ slot8,
+                                                     const int64_t *__restrict__ indptr, double *__restrict__ values) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int64_t rs = indptr[r], re = indptr[r + 1];
+    for (int64_t k = rs; k < re; ++k) values[k] = 0.0;
+    for (int64_t p = r2e_ptr[r]; p < r2e_ptr[r + 1]; ++p) {
+        const int32_t code = r2e_idx[p];
+        const unsigned long long sl = slot8[p];
+        const int64_t e = code >> 3;
+        const int l = code & 7;
+        MorleyFrame F;
+        morley_frame(pxy[t[e]], pxy[t[nt + e]], pxy[t[2 * nt + e]], F);
+        double row[6] = {0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < nq; ++q) {
+            const double xi = XW[q], eta = XW[nq + q], w = XW[2 * nq + q] * 2.0 * F.area;
+            const double lam[3] = {1.0 - xi - eta, xi, eta};
+            const double vl = morley_value(F, l, lam) * w;
+            for (int j = 0; j < 6; ++j) row[j] += vl * morley_value(F, j, lam);
+        }
+        for (int j = 0; j < 6; ++j) values[rs + ((sl >> (8 * j)) & 0xffull)] += row[j];
+    }
+}
+
+__global__ void k_morley_load_vector(int64_t nrows, int64_t nt, int nq, const double *__restrict__ XW,
+                                     const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
+                                     const int64_t *__restrict__ r2e_ptr, const int32_t *__restrict__ r2e_idx,
+                                     const double *__restrict__ fq, double *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    double acc = 0.0;
+    for (int64_t p = r2e_ptr[r]; p < r2e_ptr[r + 1]; ++p) {
+        const int32_t code = r2e_idx[p];
+        const int64_t e = code >> 3;
+        MorleyFrame F;
+        morley_frame(pxy[t[e]], pxy[t[nt + e]], pxy[t[2 * nt + e]], F);
+        double s = 0.0;
+        for (int q = 0; q < nq; ++q) {
+            const double xi = XW[q], eta = XW[nq + q], w = XW[2 * nq + q] * 2.0 * F.area;
+            const double lam[3] = {1.0 - xi - eta, xi, eta};
+            s += fq[e * nq + q] * morley_value(F, code & 7, lam) * w;
+        }
+        acc += s;
+    }
+    out[r] = acc;
+}
+
 __global__ void k_fold3(int64_t nb, const double *__restrict__ partials, double *__restrict__ out) {
     __shared__ double sh[32];
     for (int c = 0; c < 3; ++c) {
@@ -328,6 +381,28 @@ extern "C" int mwx_morley_error_sums(int64_t nt, int32_t nq, const double *xw, c
     k_morley_errors<<<(unsigned)nb, 128, 0, st>>>(nt, nq, xw, (const double2 *)pxy, t, edofs, uh, exact6, partials.p);
     MWX_LAUNCH_CHECK();
     k_fold3<<<1, 1024, 0, st>>>(nb, partials.p, sums3);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_assemble_morley_mass(int64_t nrows, int64_t nt, int32_t nq, const double *xw, const double *pxy,
+                                        const int32_t *t, const int64_t *r2e_ptr, const int32_t *r2e_idx,
+                                        const uint8_t *slot8, const int64_t *indptr, double *values, void *stream) {
+    if (nrows <= 0 || nt <= 0 || nq <= 0 || !xw || !pxy || !t || !r2e_ptr || !r2e_idx || !slot8 || !indptr || !values)
+        return MWX_E_BADARG;
+    k_morley_mass<<<grid_for(nrows, 128), 128, 0, as_stream(stream)>>>(nrows, nt, nq, xw, (const double2 *)pxy, t, r2e_ptr,
+                                                                     r2e_idx, (const unsigned long long *)slot8, indptr,
+                                                                     values);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_morley_load_vector(int64_t nrows, int64_t nt, int32_t nq, const double *xw, const double *pxy,
+                                      const int32_t *t, const int64_t *r2e_ptr, const int32_t *r2e_idx,
+                                      const double *fq, double *out, void *stream) {
+    if (nrows <= 0 || nt <= 0 || nq <= 0 || !xw || !pxy || !t || !r2e_ptr || !r2e_idx || !fq || !out) return MWX_E_BADARG;
+    k_morley_load_vector<<<grid_for(nrows, 128), 128, 0, as_stream(stream)>>>(nrows, nt, nq, xw, (const double2 *)pxy, t,
+                                                                            r2e_ptr, r2e_idx, fq, out);
     MWX_LAUNCH_CHECK();
     return 0;
 }

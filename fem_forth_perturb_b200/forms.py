@@ -11,9 +11,10 @@ Descriptors form a small algebra so that ``eps**2 * a_load + b_load`` assembles 
 
 INTERIOR = ('a_load', 'b_load')
 LAGRANGE = ('laplace',)          # grad.grad on P1 / P2 (w-problem)
+MASS = ('mass',)                 # u v on the Morley basis (L2 projection of example 3)
 MIXED = ('wv_load',)             # grad(w_h) . grad(v) with w in P1/P2, v Morley (applied, not stored)
 FACET = ('penalty_1', 'penalty_2', 'penalty_3')
-KNOWN = INTERIOR + FACET + LAGRANGE + MIXED
+KNOWN = INTERIOR + FACET + LAGRANGE + MIXED + MASS
 
 
 class BilinearFormGPU:
@@ -55,6 +56,8 @@ class BilinearFormGPU:
             return 'lagrange'
         if names <= set(MIXED):
             return 'mixed'
+        if names <= set(MASS):
+            return 'mass'
         raise NotImplementedError("interior and facet integrands need different bases; assemble them "
                                   "separately and add the matrices (as ref main/example1/run.py:260 does)")
 
@@ -68,6 +71,7 @@ penalty_1 = BilinearFormGPU({'penalty_1': 1.0}, 'penalty_1')  # ref run.py:134-1
 penalty_2 = BilinearFormGPU({'penalty_2': 1.0}, 'penalty_2')  # ref run.py:139-141
 penalty_3 = BilinearFormGPU({'penalty_3': 1.0}, 'penalty_3')  # ref run.py:144-146 (sigma passed to asm_gpu)
 laplace = BilinearFormGPU({'laplace': 1.0}, 'laplace')        # ref run.py:149-154 (P1 / P2 bases)
+mass = BilinearFormGPU({'mass': 1.0}, 'mass')                 # skfem.models.poisson.mass on the Morley basis
 wv_load = BilinearFormGPU({'wv_load': 1.0}, 'wv_load')        # ref run.py:126-131 (trial P1/P2, test Morley)
 
 

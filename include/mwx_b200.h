@@ -247,6 +247,14 @@ int mwx_morley_error_sums(int64_t nt, int32_t nq, const double *xw, const double
                           const int32_t *edofs, const double *uh, const double *exact6, double *sums3,
                           void *stream);
 
+/* project(exact_u, basis_to=basis['u']) of example 3 (ref main/example3/run.py:66, main/example3/utils.py:494-565):
+ * Morley mass matrix (quadrature, same pattern as K2) and the load vector int f phi_r (f sampled at the points). */
+int mwx_assemble_morley_mass(int64_t nrows, int64_t nt, int32_t nq, const double *xw, const double *pxy,
+                             const int32_t *t, const int64_t *r2e_ptr, const int32_t *r2e_idx,
+                             const uint8_t *slot8, const int64_t *indptr, double *values, void *stream);
+int mwx_morley_load_vector(int64_t nrows, int64_t nt, int32_t nq, const double *xw, const double *pxy,
+                           const int32_t *t, const int64_t *r2e_ptr, const int32_t *r2e_idx, const double *fq,
+                           double *out, void *stream);
 /* L2pnvError, ref run.py:106-108,527: terms[b] = int_F (h_F n . grad u_h)^2 for each listed boundary facet. */
 int mwx_morley_facet_pnv(int64_t nt, int64_t nbf, const double *pxy, const int32_t *t, const int32_t *edofs,
                          const int32_t *btri, const int32_t *blocal, const double *uh, double *terms,

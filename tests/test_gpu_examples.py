@@ -97,3 +97,32 @@ def test_penalty_example_tables_match_reference_logs(cuda, golden_norms):
         rel = np.abs(tab - gold) / np.abs(gold)
         assert rel.max() < 5e-4, (eps, rel)
         assert rel[0].max() < 1e-7                                # level 1: 17 unknowns, CG tolerance 1e-8
+
+
+def test_example3_lshape_tables_match_reference_log(cuda, golden_norms):
+    """examples/example3.py = main/example3/run.py as shipped (L-shape, inhomogeneous data through a global L2
+    projection, tol 1e-11, intorder 8) vs main/example3/log/ex4_P1_nopen_2021-02-22_12-51-55.csv."""
+    sys.path.insert(0, os.path.join(ROOT, 'examples'))
+    import example3
+    results = example3.run(refine_time=5, out=lambda *a: None)
+    g = golden_norms['ex4_P1_nopen']
+    for eps, tab in results.items():
+        gold = np.array(g['rows'][repr(float(eps))][:5])
+        rel = np.abs(tab - gold) / np.abs(gold)
+        assert rel.max() < 5e-4, (eps, rel)                       # 3 significant digits
+        assert rel[0].max() < 1e-9                                # level 1
+
+
+def test_project_is_the_l2_projection(cuda):
+    import fem_forth_perturb_b200 as F
+    gm = F.MeshTri.init_lshaped().refine(3)
+    ub = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=8)
+    om = OMesh.init_lshaped().refine(3)
+    ub_o = OInterior(om, 'Morley', 8, shift=True)
+    prob = pl.Ex4(1e-5)
+    M_o = oa.asm_bilinear(oa.mass, ub_o)
+    x_o = pl.spl.spsolve(M_o.tocsc(), oa.asm_linear(prob.u, ub_o))
+    M = F.asm_gpu(F.mass, ub).tocsr()
+    assert abs(M - M_o).max() <= 1e-12 * abs(M_o).max()
+    x = F.project(prob.u, ub)
+    assert np.linalg.norm(x - x_o) <= 1e-10 * np.linalg.norm(x_o)

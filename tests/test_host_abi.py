@@ -61,10 +61,10 @@ def test_form_dispatch_is_by_name_and_rejects_unknown():
             self.form = fn
     assert F.as_form(SkfemLike(a_load)).terms == {'a_load': 1.0}
 
-    def mass(u, v, w):
+    def linear_elasticity(u, v, w):
         return None
     with pytest.raises(NotImplementedError):
-        F.as_form(mass)
+        F.as_form(linear_elasticity)
     with pytest.raises(NotImplementedError):
         (F.a_load + F.penalty_1).kind
 
