@@ -473,26 +473,44 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
     n_global = parts[0].partition.n
     if maxiter is None or maxiter <= 0:
         maxiter = 10 * n_global
-    S = []
-    for p, b in zip(parts, b_list):
-        dev = b.device
+    # Per-part CG state.  It is cached on the parts (keyed by communicator / preconditioner) so that repeated solves
+    # reuse the symmetric-memory vectors.
+    key = (id(comm), precond, id(amg), id(ops))
+    cache = getattr(parts[0], '_cg_state', None)
+    if cache is None or cache['key'] != key or len(cache['S']) != len(parts):
+        S = []
+        for p, b in zip(parts, b_list):
+            dev = b.device
+            S.append(dict(b=ops.zeros(p.nloc, dev), ws=ops.workspace(dev), x=comm.ext_zeros(p, dev),
+                          p=comm.ext_zeros(p, dev), r=ops.zeros(p.nloc, dev), q=ops.zeros(p.nloc, dev), z=None,
+                          dinv=None))
+        cache = dict(key=key, S=S)
+        parts[0]._cg_state = cache
+    S = cache['S']
+    for p, st, b in zip(parts, S, b_list):
         p.ops = ops
-        cache = getattr(p, '_cg_ext', None)              # ext vectors are reused across solves (symmetric memory)
-        if cache is None or cache[0] is not comm:
-            cache = (comm, comm.ext_zeros(p, dev), comm.ext_zeros(p, dev))
-            p._cg_ext = cache
-        cache[1].zero_(); cache[2].zero_()
-        st = dict(b=b, ws=ops.workspace(dev), x=cache[1], p=cache[2],
-                  r=b.clone(), q=ops.zeros(p.nloc, dev), z=None,
-                  dinv=ops.diag_inv(p) if precond == 'jacobi' else None)
-        S.append(st)
+        st['b'].copy_(b)
+        st['r'].copy_(b)
+        st['x'].zero_(); st['p'].zero_(); st['ws'].zero_()
+        st['dinv'] = ops.diag_inv(p) if precond == 'jacobi' else None
     jacobi = precond in ('jacobi', 'none')
 
+    slot_index = {}
+
     def reduce_slots(slots):
-        packs = [st['ws'][slots].clone() for st in S]
+        """All-reduce the listed scalar slots of every part's workspace (device-side gather/scatter of the slots:
+        no host tensors involved, so the call is CUDA-graph capturable)."""
+        key = tuple(slots)
+        packs = []
+        for st in S:
+            dev_key = (key, st['ws'].device)
+            if dev_key not in slot_index:
+                import torch
+                slot_index[dev_key] = torch.tensor(list(key), dtype=torch.int64, device=st['ws'].device)
+            packs.append(st['ws'].index_select(0, slot_index[dev_key]))
         comm.allreduce_sum(packs)
         for st, pk in zip(S, packs):
-            st['ws'][slots] = pk
+            st['ws'].index_copy_(0, slot_index[(key, st['ws'].device)], pk)
         return packs[0]
 
     for p, st in zip(parts, S):
@@ -507,7 +525,9 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
             ops.residual(p, st['x'], st['b'], st['r'], st['dinv'], st['ws'])
         reduce_slots([SLOT_RHO, SLOT_RR])
     resid = bnrm
-    for it in range(1, maxiter + 1):
+
+    def iteration(first):
+        """One CG iteration: kernels, halo exchanges and all-reduces only - no host read-back (graph-capturable)."""
         if not jacobi:
             zs = amg.apply([st['r'] for st in S]) if hasattr(amg, 'apply') else [h.precondition(st['r']) for h, st in zip(amg, S)]
             for p, st, z in zip(parts, S, zs):
@@ -515,14 +535,20 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
                 ops.dot(p.nloc, st['r'], st['z'], st['ws'], SLOT_RHO)
             reduce_slots([SLOT_RHO])
         for p, st in zip(parts, S):
-            ops.p_update(p.nloc, st['r'], st['dinv'], st['z'] if not jacobi else None, st['p'], st['ws'], it == 1)
+            ops.p_update(p.nloc, st['r'], st['dinv'], st['z'] if not jacobi else None, st['p'], st['ws'], first)
         comm.halo(parts, [st['p'] for st in S])
         for p, st in zip(parts, S):
             ops.spmv_dot(p, st['p'], st['q'], st['ws'])
         reduce_slots([SLOT_PQ])
         for p, st in zip(parts, S):
             ops.xr_update(p.nloc, st['p'], st['q'], st['x'], st['r'], st['dinv'], st['ws'], jacobi)
-        red = reduce_slots([SLOT_RHO, SLOT_RR] if jacobi else [SLOT_RR])
+        reduce_slots([SLOT_RHO, SLOT_RR] if jacobi else [SLOT_RR])
+
+    # (A CUDA-graph replay of `iteration` was tried: capture works, but replayed symmetric-memory barriers mixed
+    #  with eager ones deadlock, and a per-solve capture costs more than the ~0.5 ms of launches it saves.)
+    for it in range(1, maxiter + 1):
+        iteration(it == 1)
+        red = [S[0]['ws'][SLOT_RR]]
         resid = math.sqrt(float(red[-1]))
         if resid != resid:
             return xs(), it, it, resid
