@@ -30,6 +30,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 EPS = 1e-2            # eps^2 = 1e-4 (SURVEY 8d microbench setting)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the SAME
+# kernels on the level-12 workload (profiles/r01_ncu_final_spmv_assembly.txt); None for other levels.
+NCU_TRAFFIC_BYTES = {12: {'k_spmv': 10.374417e9 + 0.536002e9, 'k_assemble_morley': 12.214540e9 + 6.146322e9}}
 TOL = 1e-8            # the reference's tol (ref main/example1/run.py:20)
 
 
@@ -349,10 +352,12 @@ def main():
         'setup_s': {'mesh_refine': t_mesh, 'pattern_slotmap': t_pattern, 'condense_plan': t_cplan, 'amg_host_rs': ml.setup_host_seconds,
                     'amg_upload': ml.upload_seconds, 'amg_reorder': ml.reorder_seconds, 'amg_total': t_amg},
         'roofline': {'kernel': 'k_spmv (CSR SpMV, fine level, solver numbering)', 'bound': 'hbm', 'achieved': spmv_gbs, 'peak': peak,
-                     'unit': 'GB/s', 'frac': spmv_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                     'unit': 'GB/s', 'frac': spmv_gbs / peak,
+                     'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_spmv'), 'peak_source': peak_src,
                      'algorithmic_bytes': spmv_bytes},
         'roofline_assembly': {'kernel': 'k_assemble_morley', 'bound': 'hbm', 'achieved': asm_gbs, 'peak': peak,
-                              'unit': 'GB/s', 'frac': asm_gbs / peak, 'traffic': None,
+                              'unit': 'GB/s', 'frac': asm_gbs / peak,
+                              'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_assemble_morley'),
                               'algorithmic_bytes': asm_bytes},
         'e2e': {'value': units / (e2e_ms / args.steps * 1e-3) / 1e6, 'unit': 'MDOF/s',
                 'h2d_bytes_per_step': int(p_host.numel() * 8 + t_host.numel() * 4 + b_host.numel() * 8),
