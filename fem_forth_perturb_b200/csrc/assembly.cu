@@ -184,11 +184,14 @@ __global__ void k_element_geometry(int64_t nt, const double2 *__restrict__ pxy, 
 
 constexpr int ASM_MAXP = 8;               // (row, element) pairs per row staged in shared memory
 
+// The 64-byte record is fetched with two 256-bit loads (sm_100 LDG.E.256: one 32-byte sector per thread and
+// instruction).  Every thread of a warp reads a different record, so L1 handles one tag per thread per load:
+// two instead of the four a 128-bit load sequence needs - the kernel's busiest unit is L1tex.
 __device__ __forceinline__ MorleyGeom load_geom(const double2 *__restrict__ exy, int64_t e) {
-    const double2 ra = __ldg(exy + 4 * e), rb = __ldg(exy + 4 * e + 1), rc = __ldg(exy + 4 * e + 2),
-                  rd = __ldg(exy + 4 * e + 3);
+    const double *p = reinterpret_cast<const double *>(exy + 4 * e);
     MorleyGeom G;
-    G.g0 = ra.x; G.g1 = ra.y; G.g2 = rb.x; G.m01 = rb.y; G.m02 = rc.x; G.m12 = rc.y; G.area = rd.x; G.pad = 0.0;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(G.g0), "=d"(G.g1), "=d"(G.g2), "=d"(G.m01) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(G.m02), "=d"(G.m12), "=d"(G.area), "=d"(G.pad) : "l"(p + 4));
     return G;
 }
 
