@@ -339,6 +339,18 @@ def test_amg_pcg_iteration_counts_match_reference_log(cuda, golden_iterations):
         assert all(abs(a - b) <= slack for a, b in zip(mine, gold)), (eps_s, mine, gold)
 
 
+@pytest.mark.parametrize('level,eps', [(7, 1e-2), (7, 1e-4), (8, 1e-2), (8, 1e-4)])
+def test_amg_pcg_iteration_counts_levels_7_8(cuda, golden_iterations, level, eps):
+    """The larger rows of the reference's table (66 049 and 263 169 DOFs): parity mode within +-1 of the log."""
+    import fem_forth_perturb_b200 as F
+    om = OMesh().refine(level)
+    S = pl.solve_problem(om, pl.Ex1(eps), wkind='P1', intorder=5, return_system=True)
+    solver = F.solver_iter_mgcg(tol=1e-8, maxiter=1000)
+    x, it = solver.solve_with_info(S['Kc'], S['bc'])
+    gold = golden_iterations['u'][repr(float(eps))][level - 1]
+    assert solver.last['info'] == 0 and abs(it - gold) <= 1, (level, eps, it, gold)
+
+
 @pytest.mark.parametrize('mode', ['chebyshev', 'jacobi'])
 def test_amg_fast_modes_converge_to_the_same_solution(cuda, mode):
     import fem_forth_perturb_b200 as F
