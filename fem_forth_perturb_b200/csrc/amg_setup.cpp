@@ -19,6 +19,9 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -293,18 +296,33 @@ extern "C" int mwx_amg_setup_host(int64_t n, const int64_t *indptr, const int32_
         A0.ptr.assign(indptr, indptr + n + 1);
         A0.idx.assign(indices, indices + indptr[n]);
         A0.val.assign(values, values + indptr[n]);
+        const bool prof = std::getenv("MWX_AMG_PROFILE") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double>(b - a).count();
+        };
         while ((int32_t)h->levels.size() < max_levels && h->levels.back().A.rows > max_coarse) {
             Level &L = h->levels.back();
             Graph S, T;
             std::vector<uint8_t> strong;
+            const auto t0 = now();
             strength_graph(L.A, theta, S, strong);
+            const auto t1 = now();
             transpose_graph(S, L.A.rows, T);
+            const auto t2 = now();
             rs_first_pass(L.A.rows, S, T, L.split);
+            const auto t3 = now();
             direct_interpolation(L.A, strong, L.split, L.P);
             if (L.P.cols == 0) break;                      // nothing left to coarsen
             transpose_csr(L.P, L.R);
+            const auto t4 = now();
             Level next;
             galerkin(L.R, L.A, L.P, next.A);
+            const auto t5 = now();
+            if (prof)
+                std::fprintf(stderr, "[mwx amg] level %zu n=%lld: strength %.3f transpose %.3f split %.3f interp+R %.3f galerkin %.3f s\n",
+                             h->levels.size() - 1, (long long)L.A.rows, secs(t0, t1), secs(t1, t2), secs(t2, t3),
+                             secs(t3, t4), secs(t4, t5));
             h->levels.push_back(std::move(next));
         }
     } catch (const std::bad_alloc &) {
