@@ -44,6 +44,7 @@ _SIGNATURES = {
     'mwx_dist_rows_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_dist_localize': [i64, vp, i32, i32, vp, i32, i32, vp, vp],
     'mwx_gather_f64_i64': [i64, vp, vp, vp, vp],
+    'mwx_halo_push': [i64, i32, vp, vp, vp, vp, vp],
     'mwx_dcg_workspace_doubles': [],
     'mwx_dcg_dot': [i64, vp, vp, vp, i32, vp],
     'mwx_dcg_p_update': [i64, vp, vp, vp, vp, vp, i32, vp],

@@ -16,7 +16,10 @@
 // Algorithmic bytes per element (the figure bench.py's roofline uses):
 //   read  incidence codes 6*4 = 24, slot map 6*8 = 48, t 12, coordinates ~8, indptr+r2e_ptr ~32
 //   write CSR values 23*8 = 184                                                   => 308 B/element
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mwx {
 namespace {
@@ -74,6 +77,10 @@ __global__ void __launch_bounds__(128) k_pattern_fill(int64_t ndofs, int64_t nt,
     const int n = gather_row_cols(r, nt, ndpe, edofs, r2e_ptr, r2e_idx, cols);
     const int64_t s = indptr[r];
     for (int k = 0; k < n; ++k) indices[s + k] = cols[k];
+    // Byte j of a pair's word = CSR slot (within the row) of the element's j-th DOF.  With at most six DOFs per
+    // element, byte 7 carries a mask: bit j set = an EARLIER pair of this row already wrote that slot, so this
+    // pair adds to it; clear = first touch, a plain store (the assembly kernels then need no zero-fill pass).
+    unsigned long long seen[4] = {0ull, 0ull, 0ull, 0ull};
     for (int64_t p = r2e_ptr[r]; p < r2e_ptr[r + 1]; ++p) {
         const int64_t e = r2e_idx[p] >> 3;
         unsigned long long w = 0;
@@ -85,6 +92,11 @@ __global__ void __launch_bounds__(128) k_pattern_fill(int64_t ndofs, int64_t nt,
                 if (cols[mid] < c) lo = mid + 1; else hi = mid;
             }
             w |= (unsigned long long)(unsigned)lo << (8 * j);
+            if (ndpe <= 6) {
+                const unsigned long long bit = 1ull << (lo & 63);
+                if (seen[lo >> 6] & bit) w |= 1ull << (56 + j);
+                seen[lo >> 6] |= bit;
+            }
         }
         slot8[p] = w;
     }
@@ -182,7 +194,8 @@ __global__ void k_element_geometry(int64_t nt, const double2 *__restrict__ pxy, 
     exy[4 * e + 3] = make_double2(G.area, 0.0);
 }
 
-constexpr int ASM_MAXP = 8;               // (row, element) pairs per row staged in shared memory
+constexpr int ASM_MAXP = 8;               // (row, element) pairs per row staged in shared memory (row-list mode)
+constexpr int ASM_PAIRS = ASM_MAXP * ASM_ROWS;   // pair words staged per CTA
 
 // The 64-byte record is fetched with two 256-bit loads (sm_100 LDG.E.256: one 32-byte sector per thread and
 // instruction).  Every thread of a warp reads a different record, so L1 handles one tag per thread per load:
@@ -195,20 +208,22 @@ __device__ __forceinline__ MorleyGeom load_geom(const double2 *__restrict__ exy,
     return G;
 }
 
-// One thread owns one matrix row.  Its incidence codes and slot words (contiguous per row) are fetched in one
-// burst into shared memory; the 64-byte geometry record of pair q+1 is in flight while pair q is evaluated;
-// the six slot updates of a pair (distinct columns) are issued as six loads, six adds, six stores on the
-// shared-memory image of the row.  Rows are summed in ascending element order - no atomics, bit-reproducible.
+// One thread owns one matrix row.  The tile's incidence codes and slot words - one contiguous range of the
+// row-to-element arrays - are copied coalesced into shared memory (row-list mode: each thread stages its own
+// row's run); the 64-byte geometry record of pair q+1 is in flight while pair q is evaluated; the six slot
+// updates of a pair (distinct columns) go to the shared-memory image of the row: a plain store where the slot
+// map says "first touch", load-add-store otherwise, so the image needs no zero-fill.  Rows are summed in
+// ascending element order - no atomics, bit-reproducible.
 template <bool ROWLIST>
-__global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
+__global__ void __launch_bounds__(ASM_ROWS, 6) k_assemble_morley(
     int64_t nrows, int64_t nt, const double2 *__restrict__ exy,
     const int64_t *__restrict__ r2e_ptr, const int32_t *__restrict__ r2e_idx,
     const unsigned long long *__restrict__ slot8, const int64_t *__restrict__ indptr,
     const int32_t *__restrict__ row_ids, const int64_t *__restrict__ out_indptr,
     double ca, double cb, int accumulate, double *__restrict__ values) {
     __shared__ double acc[ASM_CAP];
-    __shared__ unsigned long long s_slot[ASM_MAXP][ASM_ROWS];
-    __shared__ int32_t s_code[ASM_MAXP][ASM_ROWS];
+    __shared__ unsigned long long s_slot[ASM_PAIRS];
+    __shared__ int32_t s_code[ASM_PAIRS];
     const int64_t *optr = ROWLIST ? out_indptr : indptr;
     const int64_t i0 = (int64_t)blockIdx.x * ASM_ROWS;
     const int64_t i1 = i0 + ASM_ROWS < nrows ? i0 + ASM_ROWS : nrows;
@@ -221,22 +236,37 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
     int64_t pb = 0;
     int np = 0;
     int64_t rs = 0;
-    if (i < i1) {
-        const int64_t r = ROWLIST ? (int64_t)row_ids[i] : i;
-        pb = r2e_ptr[r];
-        np = (int)(r2e_ptr[r + 1] - pb);
-        rs = optr[i];
-#pragma unroll
-        for (int q = 0; q < ASM_MAXP; ++q)
-            if (q < np) {
-                s_code[q][tid] = __ldg(r2e_idx + pb + q);
-                s_slot[q][tid] = __ldg(slot8 + pb + q);
+    int mbase = 0, mstride = 1, mcount = 0;      // this row's staged pair words: s_*[mbase + q * mstride], q < mcount
+    if (ROWLIST) {
+        if (i < i1) {
+            const int64_t r = (int64_t)row_ids[i];
+            pb = r2e_ptr[r];
+            np = (int)(r2e_ptr[r + 1] - pb);
+            rs = optr[i];
+            mbase = tid; mstride = ASM_ROWS; mcount = np < ASM_MAXP ? np : ASM_MAXP;
+            for (int q = 0; q < mcount; ++q) {
+                s_code[q * ASM_ROWS + tid] = __ldg(r2e_idx + pb + q);
+                s_slot[q * ASM_ROWS + tid] = __ldg(slot8 + pb + q);
             }
+        }
+    } else {
+        const int64_t pb0 = r2e_ptr[i0], pb1 = r2e_ptr[i1];
+        const bool flat = pb1 - pb0 <= ASM_PAIRS;             // CTA-uniform
+        if (flat) {
+            const int cnt = (int)(pb1 - pb0);
+            for (int k = tid; k < cnt; k += ASM_ROWS) {
+                s_code[k] = __ldg(r2e_idx + pb0 + k);
+                s_slot[k] = __ldg(slot8 + pb0 + k);
+            }
+        }
+        if (i < i1) {
+            pb = r2e_ptr[i];
+            np = (int)(r2e_ptr[i + 1] - pb);
+            rs = optr[i];
+            if (flat) { mbase = (int)(pb - pb0); mcount = np; }
+        }
     }
-    if (staged) {
-        for (int k = tid; k < (int)len; k += ASM_ROWS) acc[k] = 0.0;
-        __syncthreads();
-    }
+    __syncthreads();
     if (i < i1) {
         if (!staged && !accumulate) {
             const int64_t re = optr[i + 1];
@@ -244,21 +274,26 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
         }
         double *arow = acc + (rs - s0);
         MorleyGeom G;
-        if (np > 0) G = load_geom(exy, (int64_t)(s_code[0][tid] >> 3));
+        int32_t code = 0;
+        if (np > 0) {
+            code = 0 < mcount ? s_code[mbase] : __ldg(r2e_idx + pb);
+            G = load_geom(exy, (int64_t)(code >> 3));
+        }
         for (int q = 0; q < np; ++q) {
-            const int32_t code = q < ASM_MAXP ? s_code[q][tid] : __ldg(r2e_idx + pb + q);
-            const unsigned long long sl = q < ASM_MAXP ? s_slot[q][tid] : __ldg(slot8 + pb + q);
+            const unsigned long long sl = q < mcount ? s_slot[mbase + q * mstride] : __ldg(slot8 + pb + q);
             const MorleyGeom Gc = G;
+            const int l = code & 7;
             if (q + 1 < np) {                      // next pair's record is in flight during this pair's math
-                const int32_t cn = q + 1 < ASM_MAXP ? s_code[q + 1][tid] : __ldg(r2e_idx + pb + q + 1);
-                G = load_geom(exy, (int64_t)(cn >> 3));
+                code = q + 1 < mcount ? s_code[mbase + (q + 1) * mstride] : __ldg(r2e_idx + pb + q + 1);
+                G = load_geom(exy, (int64_t)(code >> 3));
             }
             double row[6];
-            morley_local_row(Gc, code & 7, ca, cb, row);
+            morley_local_row(Gc, l, ca, cb, row);
             if (staged) {
+                const unsigned rm = (unsigned)(sl >> 56);
                 double o[6];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) o[j] = arow[(sl >> (8 * j)) & 0xffull];
+                for (int j = 0; j < 6; ++j) o[j] = (rm >> j) & 1u ? arow[(sl >> (8 * j)) & 0xffull] : 0.0;
 #pragma unroll
                 for (int j = 0; j < 6; ++j) arow[(sl >> (8 * j)) & 0xffull] = o[j] + row[j];
             } else {
@@ -273,6 +308,168 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley(
             for (int k = tid; k < (int)len; k += ASM_ROWS) values[s0 + k] += acc[k];
         else
             for (int k = tid; k < (int)len; k += ASM_ROWS) values[s0 + k] = acc[k];
+    }
+}
+
+// ---- whole-matrix assembly: persistent, software-pipelined form of the kernel above ---------------------------
+// The row kernel above is bound by a CHAIN of dependent DRAM latencies per CTA (tile bounds -> pair words ->
+// first record -> ... ; ncu: 55 % of warp time on long_scoreboard, DRAM 36 %, L1 74 %) rather than by bytes.
+// Here CTAs are persistent (occupancy x 148) and stride over the 128-row tiles with everything a tile needs
+// fetched one tile ahead, asynchronously:
+//   * the tile's pair words (incidence codes + slot words: one contiguous range each) by two TMA bulk copies
+//     issued by one thread (mbarrier complete_tx), their range bounds loaded one further tile ahead;
+//   * its row pointers (r2e_ptr, indptr segments) by per-thread 8-byte cp.async;
+//   * and inside a tile each thread keeps TWO geometry records in flight.
+struct AsmStage {
+    unsigned long long slot[ASM_PAIRS + 2];      // staged from an even pair index (16-byte aligned source)
+    int32_t code[ASM_PAIRS + 8];                 // staged from a multiple-of-4 pair index
+    int64_t rptr[ASM_ROWS + 2];                  // r2e_ptr[i0 .. i1]
+    int64_t optr[ASM_ROWS + 2];                  // indptr[i0 .. i1]
+};
+static_assert(sizeof(AsmStage) % 16 == 0, "stage must keep 16-byte alignment");
+constexpr int ASMP_SMEM_BYTES = ASM_CAP * 8 + 2 * (int)sizeof(AsmStage) + 64;
+
+__global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
+    int64_t nrows, const double2 *__restrict__ exy, const int64_t *__restrict__ r2e_ptr,
+    const int32_t *__restrict__ r2e_idx, const unsigned long long *__restrict__ slot8,
+    const int64_t *__restrict__ indptr, double ca, double cb, int accumulate, double *__restrict__ values,
+    int tma_ok) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *acc = reinterpret_cast<double *>(smem_raw);
+    AsmStage *stg = reinterpret_cast<AsmStage *>(smem_raw + ASM_CAP * 8);
+    unsigned char *tail = smem_raw + ASM_CAP * 8 + 2 * sizeof(AsmStage);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tail);                  // [2]
+    int64_t *s_cb0 = reinterpret_cast<int64_t *>(tail + 16);            // [2] first staged code index
+    int64_t *s_sb0 = reinterpret_cast<int64_t *>(tail + 32);            // [2] first staged slot-word index
+    int32_t *s_flat = reinterpret_cast<int32_t *>(tail + 48);           // [2] pair words staged by TMA?
+
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (nrows + ASM_ROWS - 1) / ASM_ROWS;
+    int64_t npairs = 0;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+        npairs = r2e_ptr[nrows];
+    }
+    auto bounds = [&](int64_t tile, int64_t &a, int64_t &b) {
+        const int64_t i0 = tile * ASM_ROWS;
+        const int64_t i1 = i0 + ASM_ROWS < nrows ? i0 + ASM_ROWS : nrows;
+        a = r2e_ptr[i0];
+        b = r2e_ptr[i1];
+    };
+    auto issue = [&](int64_t pb0, int64_t pb1, int stage) {              // thread 0
+        const int64_t cb0 = pb0 & ~(int64_t)3, ce = (pb1 + 3) & ~(int64_t)3;
+        const int64_t sb0 = pb0 & ~(int64_t)1, se = (pb1 + 1) & ~(int64_t)1;
+        if (tma_ok && pb1 > pb0 && pb1 - pb0 <= ASM_PAIRS && ce <= npairs && se <= npairs) {
+            s_cb0[stage] = cb0;
+            s_sb0[stage] = sb0;
+            s_flat[stage] = 1;
+            fence_proxy_async();
+            mbar_expect_tx(&bar[stage], (uint32_t)((ce - cb0) * 4 + (se - sb0) * 8));
+            bulk_g2s(stg[stage].code, r2e_idx + cb0, (uint32_t)((ce - cb0) * 4), &bar[stage]);
+            bulk_g2s(stg[stage].slot, slot8 + sb0, (uint32_t)((se - sb0) * 8), &bar[stage]);
+        } else {
+            s_flat[stage] = 0;
+        }
+    };
+    auto fetch_ptrs = [&](int64_t tile, int stage) {                     // all threads
+        const int64_t i0 = tile * ASM_ROWS;
+        const int64_t cnt = (i0 + ASM_ROWS < nrows ? ASM_ROWS : nrows - i0) + 1;   // entries i0 .. i1
+        if (tid < cnt) {
+            cp_async_8(&stg[stage].rptr[tid], r2e_ptr + i0 + tid);
+            cp_async_8(&stg[stage].optr[tid], indptr + i0 + tid);
+        }
+        if (tid == 0 && cnt == ASM_ROWS + 1) {
+            cp_async_8(&stg[stage].rptr[ASM_ROWS], r2e_ptr + i0 + ASM_ROWS);
+            cp_async_8(&stg[stage].optr[ASM_ROWS], indptr + i0 + ASM_ROWS);
+        }
+        cp_async_commit();
+    };
+
+    int64_t tile = blockIdx.x;
+    int64_t nb0 = 0, nb1 = 0;                 // thread 0: pair range of the NEXT tile, loaded one iteration early
+    if (tile < ntiles) {
+        if (tid == 0) {
+            bounds(tile, nb0, nb1);
+            issue(nb0, nb1, 0);
+            if (tile + gridDim.x < ntiles) bounds(tile + gridDim.x, nb0, nb1);
+        }
+        fetch_ptrs(tile, 0);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+    for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+        const int stage = k & 1;
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles) {
+            if (tid == 0) {
+                issue(nb0, nb1, stage ^ 1);
+                if (next + gridDim.x < ntiles) bounds(next + gridDim.x, nb0, nb1);     // lands during this tile
+            }
+            fetch_ptrs(next, stage ^ 1);
+        }
+        const AsmStage &S = stg[stage];
+        const int64_t i0 = tile * ASM_ROWS;
+        const int nr = (int)(i0 + ASM_ROWS < nrows ? ASM_ROWS : nrows - i0);
+        const int64_t s0 = S.optr[0];
+        const int64_t len = S.optr[nr] - s0;
+        const bool staged = len <= ASM_CAP;          // CTA-uniform
+        const bool flat = s_flat[stage] != 0;        // CTA-uniform
+        if (flat) {
+            if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+            else            { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+        }
+        if (tid < nr) {
+            const int64_t pb = S.rptr[tid];
+            const int np = (int)(S.rptr[tid + 1] - pb);
+            const int64_t rs = S.optr[tid];
+            const int32_t *codes = flat ? S.code + (pb - s_cb0[stage]) : r2e_idx + pb;
+            const unsigned long long *slots = flat ? S.slot + (pb - s_sb0[stage]) : slot8 + pb;
+            if (!staged && !accumulate) {
+                const int64_t re = S.optr[tid + 1];
+                for (int64_t kk = rs; kk < re; ++kk) values[kk] = 0.0;
+            }
+            double *arow = acc + (rs - s0);
+            MorleyGeom Ga, Gb;
+            int32_t c0 = 0, c1 = 0;
+            if (np > 0) { c0 = codes[0]; Ga = load_geom(exy, (int64_t)(c0 >> 3)); }
+            if (np > 1) { c1 = codes[1]; Gb = load_geom(exy, (int64_t)(c1 >> 3)); }
+            for (int q = 0; q < np; ++q) {
+                const MorleyGeom Gc = Ga;
+                const int l = c0 & 7;
+                Ga = Gb;
+                c0 = c1;
+                if (q + 2 < np) {                  // two records in flight behind the one being evaluated
+                    c1 = codes[q + 2];
+                    Gb = load_geom(exy, (int64_t)(c1 >> 3));
+                }
+                const unsigned long long sl = slots[q];
+                double row[6];
+                morley_local_row(Gc, l, ca, cb, row);
+                if (staged) {
+                    const unsigned rm = (unsigned)(sl >> 56);
+                    double o[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) o[j] = (rm >> j) & 1u ? arow[(sl >> (8 * j)) & 0xffull] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) arow[(sl >> (8 * j)) & 0xffull] = o[j] + row[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) values[rs + ((sl >> (8 * j)) & 0xffull)] += row[j];
+                }
+            }
+        }
+        if (staged) {
+            __syncthreads();
+            if (accumulate)
+                for (int kk = tid; kk < (int)len; kk += ASM_ROWS) values[s0 + kk] += acc[kk];
+            else
+                for (int kk = tid; kk < (int)len; kk += ASM_ROWS) values[s0 + kk] = acc[kk];
+        }
+        cp_async_wait_all();             // next tile's row pointers have landed
+        __syncthreads();                 // stage and acc fully consumed before they are refilled
     }
 }
 
@@ -459,10 +656,32 @@ extern "C" int mwx_assemble_morley(int64_t ndofs, int64_t nt, const double *pxy,
         int rc = refresh_element_coords(nt, pxy, t, exy, st);
         if (rc) return rc;
     }
-    const unsigned grid = (unsigned)((ndofs + ASM_ROWS - 1) / ASM_ROWS);
-    k_assemble_morley<false><<<grid, ASM_ROWS, 0, st>>>(
-        ndofs, nt, (const double2 *)exy, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, nullptr,
-        nullptr, ca, cb, accumulate, values);
+    static const bool tile_kernel = [] { const char *e = getenv("MWX_ASM_KERNEL"); return e && !strcmp(e, "tile"); }();
+    if (tile_kernel) {                               // A/B switch: the one-CTA-per-tile kernel
+        const unsigned g = (unsigned)((ndofs + ASM_ROWS - 1) / ASM_ROWS);
+        k_assemble_morley<false><<<g, ASM_ROWS, 0, st>>>(
+            ndofs, nt, (const double2 *)exy, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, nullptr,
+            nullptr, ca, cb, accumulate, values);
+        MWX_LAUNCH_CHECK();
+        return 0;
+    }
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ASMP_SMEM_BYTES));
+        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_persistent, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int occ = 0;
+        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble_morley_persistent, ASM_ROWS,
+                                                               ASMP_SMEM_BYTES));
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    const int64_t ntiles = (ndofs + ASM_ROWS - 1) / ASM_ROWS;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    const int tma_ok = !(((uintptr_t)r2e_idx | (uintptr_t)slot8) & 15);
+    k_assemble_morley_persistent<<<grid, ASM_ROWS, ASMP_SMEM_BYTES, st>>>(
+        ndofs, (const double2 *)exy, r2e_ptr, r2e_idx, (const unsigned long long *)slot8, indptr, ca, cb, accumulate,
+        values, tma_ok);
     MWX_LAUNCH_CHECK();
     return 0;
 }

@@ -130,6 +130,26 @@ extern "C" int mwx_dist_localize(int64_t nnz, const int32_t *cols_g, int32_t lo,
     return 0;
 }
 
+// Halo push: one launch packs this rank's boundary values for ALL neighbours and stores each segment straight into
+// that neighbour's ghost range (dst[s] is a peer pointer mapped over NVLink).  seg[s]..seg[s+1] delimits segment s of idx.
+__global__ void k_halo_push(int64_t total, int32_t nseg, const int64_t *__restrict__ seg, const int32_t *__restrict__ idx,
+                            const double *__restrict__ v, double *const *__restrict__ dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t s = 0;
+        while (s + 1 < nseg && i >= seg[s + 1]) ++s;
+        dst[s][i - seg[s]] = v[idx[i]];
+    }
+}
+
+extern "C" int mwx_halo_push(int64_t total, int32_t nseg, const int64_t *seg, const int32_t *idx, const double *v,
+                             double *const *dst, void *stream) {
+    if (total < 0 || nseg < 0 || (total && (!seg || !idx || !v || !dst || nseg == 0))) return MWX_E_BADARG;
+    if (total == 0) return 0;
+    k_halo_push<<<sgrid(total), 256, 0, as_stream(stream)>>>(total, nseg, seg, idx, v, dst);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *idx, double *dst, void *stream) {
     if (n < 0 || (n && (!src || !idx || !dst))) return MWX_E_BADARG;
     if (n == 0) return 0;

@@ -15,6 +15,7 @@
 // Algorithmic bytes per SpMV: 12*nnz + 20*n  (values 8 + column 4 per nonzero;
 // indptr 4, x 8, y 8 per row - SURVEY 8d; this build reads an int64 indptr, i.e. 4 B/row more).
 #include "krylov.cuh"
+#include "tma.cuh"
 
 namespace mwx {
 namespace {
@@ -43,33 +44,6 @@ __device__ __forceinline__ bool fold_partials(double v_thread0, double *partials
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(partials + i);
     total = block_sum(s, sh);
     return true;
-}
-
-// ---- TMA bulk copy + mbarrier primitives (sm_90+/sm_100a PTX) ------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
 }
 
 // Shared-memory plan of the SpMV CTA: two stages of (values, column indices) filled by TMA.

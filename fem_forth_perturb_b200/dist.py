@@ -14,6 +14,7 @@ which is how the partitioned algorithm is checked on a single GPU (and, with a C
 the tests, under gloo on CPU).  The kernels behind ``CudaOps`` are the same ones the single-GPU solver uses.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -291,7 +292,7 @@ class TorchDistComm:
             ops.append(self.dist.P2POp(self.dist.irecv, v[p.ncol + s:p.ncol + s + c], owner, group=self.group))
         for peer, idx in p.send.items():
             buf = p._sendbuf[peer]
-            CudaOps.gather(None, v, idx, buf) if getattr(p, 'ops', None) is None else p.ops.gather(v, idx, buf)
+            (getattr(p, 'ops', None) or _default_ops()).gather(v, idx, buf)
             ops.append(self.dist.P2POp(self.dist.isend, buf, peer, group=self.group))
         if ops:
             for w in self.dist.batch_isend_irecv(ops):
@@ -355,6 +356,8 @@ class SymmMemComm(TorchDistComm):
         self.handles = {}                 # data_ptr of the local tensor -> (handle, tensor)
         self.epoch = 0
         self.last_halo = {}
+        self._plans = {}
+        self._push = L.lib().mwx_halo_push
 
     def ext_zeros(self, op, device):
         import torch
@@ -388,24 +391,57 @@ class SymmMemComm(TorchDistComm):
         self.epoch += 1
         return out
 
+    def _push_plan(self, p, v, hdl):
+        """Pre-marshalled arguments of the one-launch halo push of vector v through operator p (cached)."""
+        key = (id(p), v.data_ptr())
+        plan = self._plans.get(key)
+        if plan is None:
+            import torch
+            dev = v.device
+            peers = [peer for peer in p.send if p.send[peer].numel()]
+            counts = [p.send[peer].numel() for peer in peers]
+            seg = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), device=dev)
+            idx = torch.cat([p.send[peer] for peer in peers]) if peers else torch.empty(0, dtype=torch.int32, device=dev)
+            dst = torch.tensor([hdl.buffer_ptrs[peer] + 8 * p.push[peer] for peer in peers] or [0], dtype=torch.int64,
+                               device=dev)
+            args = (int(sum(counts)), len(peers), L.ptr(seg), L.ptr(idx), L.ptr(v), L.ptr(dst), L.stream())
+            plan = self._plans[key] = (args, (seg, idx, dst, p, v))      # keep the device arrays (and the key's objects) alive
+        return plan[0]
+
     def halo(self, parts, vecs):
         (p,), (v,) = parts, vecs
-        hdl, base = self.handles[v.data_ptr()]
-        if self.last_halo.get(v.data_ptr()) == self.epoch:        # no sync event since this vector's last halo
+        vp_ = v.data_ptr()
+        hdl, base = self.handles[vp_]
+        if self.last_halo.get(vp_) == self.epoch:                 # no sync event since this vector's last halo
             hdl.barrier(channel=0)
             self.epoch += 1
-        lib, st = L.lib(), L.stream()
-        for peer, idx in p.send.items():
-            dst = ctypes.c_void_p(hdl.buffer_ptrs[peer] + 8 * p.push[peer])
-            L.check(lib.mwx_gather_f64(idx.numel(), L.ptr(v), L.ptr(idx), dst, st), 'mwx_gather_f64 (peer push)')
+        args = self._push_plan(p, v, hdl)
+        if args[0]:
+            rc = self._push(*args)
+            if rc:
+                L.check(rc, 'mwx_halo_push')
         hdl.barrier(channel=0)
         self.epoch += 1
-        self.last_halo[v.data_ptr()] = self.epoch
+        self.last_halo[vp_] = self.epoch
 
 
 # ------------------------------------------------------------------------------------------ kernels behind the driver
 class CudaOps:
-    """The device kernels (C ABI) the partitioned CG chains; tests substitute a CPU stand-in under gloo."""
+    """The device kernels (C ABI) the partitioned CG chains; tests substitute a CPU stand-in under gloo.
+
+    Every kernel launch goes through ``_emit``.  With ``record`` set to a list the launches are not executed but
+    stored as ``(fn, ctypes-ready argument tuple)`` - :class:`DistAMG` traces its V-cycle once that way and replays
+    the tuples afterwards, which removes the per-launch argument marshalling (~15 us x ~70 launches per iteration)
+    from the partitioned solver's critical path."""
+
+    def __init__(self):
+        self.record = None
+
+    def _emit(self, what, fn, *args):
+        if self.record is not None:
+            self.record.append((fn, args, what))
+        else:
+            L.check(fn(*args), what)
 
     def workspace(self, device):
         torch = L.require_cuda()
@@ -415,7 +451,7 @@ class CudaOps:
         return L.require_cuda().zeros(n, dtype=L.require_cuda().float64, device=device)
 
     def gather(self, v, idx, out):
-        L.check(L.lib().mwx_gather_f64(idx.numel(), L.ptr(v), L.ptr(idx), L.ptr(out), L.stream()), 'mwx_gather_f64')
+        self._emit('mwx_gather_f64', L.lib().mwx_gather_f64, idx.numel(), L.ptr(v), L.ptr(idx), L.ptr(out), L.stream())
 
     def diag_inv(self, p):
         torch = L.require_cuda()
@@ -425,40 +461,50 @@ class CudaOps:
         return 1.0 / d
 
     def dot(self, n, a, b, ws, slot):
-        L.check(L.lib().mwx_dcg_dot(n, L.ptr(a), L.ptr(b), L.ptr(ws), slot, L.stream()), 'mwx_dcg_dot')
+        self._emit('mwx_dcg_dot', L.lib().mwx_dcg_dot, n, L.ptr(a), L.ptr(b), L.ptr(ws), slot, L.stream())
 
     def p_update(self, n, r, dinv, z, p_ext, ws, first):
-        L.check(L.lib().mwx_dcg_p_update(n, L.ptr(r), L.ptr(dinv), L.ptr(z), L.ptr(p_ext), L.ptr(ws), int(first),
-                                         L.stream()), 'mwx_dcg_p_update')
+        self._emit('mwx_dcg_p_update', L.lib().mwx_dcg_p_update, n, L.ptr(r), L.ptr(dinv), L.ptr(z), L.ptr(p_ext),
+                   L.ptr(ws), int(first), L.stream())
 
     def spmv_dot(self, p, x_ext, q, ws):
-        L.check(L.lib().mwx_dcg_spmv_dot(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals),
-                                         L.ptr(x_ext), L.ptr(q), L.ptr(ws), L.stream()), 'mwx_dcg_spmv_dot')
+        self._emit('mwx_dcg_spmv_dot', L.lib().mwx_dcg_spmv_dot, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
+                   L.ptr(p.vals), L.ptr(x_ext), L.ptr(q), L.ptr(ws), L.stream())
 
     def xr_update(self, n, p_ext, q, x_ext, r, dinv, ws, jacobi):
-        L.check(L.lib().mwx_dcg_xr_update(n, L.ptr(p_ext), L.ptr(q), L.ptr(x_ext), L.ptr(r), L.ptr(dinv), L.ptr(ws),
-                                          int(jacobi), L.stream()), 'mwx_dcg_xr_update')
+        self._emit('mwx_dcg_xr_update', L.lib().mwx_dcg_xr_update, n, L.ptr(p_ext), L.ptr(q), L.ptr(x_ext), L.ptr(r),
+                   L.ptr(dinv), L.ptr(ws), int(jacobi), L.stream())
 
     def residual(self, p, x_ext, b, r, dinv, ws):
-        L.check(L.lib().mwx_dcg_residual(p.nloc, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_ext), L.ptr(b),
-                                         L.ptr(r), L.ptr(dinv), L.ptr(ws), L.stream()), 'mwx_dcg_residual')
+        self._emit('mwx_dcg_residual', L.lib().mwx_dcg_residual, p.nloc, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals),
+                   L.ptr(x_ext), L.ptr(b), L.ptr(r), L.ptr(dinv), L.ptr(ws), L.stream())
 
     def spmv(self, p, x_ext, y):
-        L.check(L.lib().mwx_spmv(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_ext),
-                                 L.ptr(y), L.stream()), 'mwx_spmv')
+        self._emit('mwx_spmv', L.lib().mwx_spmv, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals),
+                   L.ptr(x_ext), L.ptr(y), L.stream())
 
     def spmv_axpy(self, p, x_ext, c, sign, y):
-        L.check(L.lib().mwx_spmv_axpy(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_ext),
-                                      L.ptr(c), int(sign), L.ptr(y), L.stream()), 'mwx_spmv_axpy')
+        self._emit('mwx_spmv_axpy', L.lib().mwx_spmv_axpy, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
+                   L.ptr(p.vals), L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
 
     def smoother_first(self, n, b, dinv, c2, x_ext, d):
-        L.check(L.lib().mwx_smoother_first(n, L.ptr(b), L.ptr(dinv), float(c2), L.ptr(x_ext), L.ptr(d), L.stream()),
-                'mwx_smoother_first')
+        self._emit('mwx_smoother_first', L.lib().mwx_smoother_first, n, L.ptr(b), L.ptr(dinv), float(c2), L.ptr(x_ext),
+                   L.ptr(d), L.stream())
 
     def smoother_step(self, p, x_in, x_out, b, dinv, d, c1, c2):
-        L.check(L.lib().mwx_smoother_step(p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals), L.ptr(x_in),
-                                          L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2), L.stream()),
-                'mwx_smoother_step')
+        self._emit('mwx_smoother_step', L.lib().mwx_smoother_step, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
+                   L.ptr(p.vals), L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2),
+                   L.stream())
+
+
+_DEFAULT_OPS = None
+
+
+def _default_ops():
+    global _DEFAULT_OPS
+    if _DEFAULT_OPS is None:
+        _DEFAULT_OPS = CudaOps()
+    return _DEFAULT_OPS
 
 
 # ------------------------------------------------------------------------------------------ the partitioned PCG
@@ -498,9 +544,13 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
     slot_index = {}
 
     def reduce_slots(slots):
-        """All-reduce the listed scalar slots of every part's workspace (device-side gather/scatter of the slots:
-        no host tensors involved, so the call is CUDA-graph capturable)."""
+        """All-reduce the listed scalar slots of every part's workspace.  A contiguous run of slots is reduced in
+        place through a view; scattered slots go through a device-side gather/scatter (no host tensors either way)."""
         key = tuple(slots)
+        if key[-1] - key[0] + 1 == len(key):
+            views = [st['ws'][key[0]:key[-1] + 1] for st in S]
+            comm.allreduce_sum(views)
+            return views[0]
         packs = []
         for st in S:
             dev_key = (key, st['ws'].device)
@@ -600,6 +650,17 @@ class BlockJacobiAMG:
         return [h.precondition(r) for h, r in zip(self.h, r_list)]
 
 
+class _DeferredComm:
+    """Routes halo exchanges through DistAMG._host_step so that they are deferred while a cycle is traced."""
+
+    def __init__(self, comm, host_step):
+        self.comm, self.host_step = comm, host_step
+
+    def halo(self, parts, vecs):
+        parts, vecs = list(parts), list(vecs)
+        self.host_step(lambda: self.comm.halo(parts, vecs))
+
+
 class DistAMG:
     """The GLOBAL Ruge-Stueben hierarchy (same C++ host setup as the single-GPU solver, built once on the root
     rank from the solver-numbered matrix) applied as a collective V(1,1) cycle.
@@ -619,6 +680,7 @@ class DistAMG:
             raise NotImplementedError("the partitioned V-cycle implements the Chebyshev smoother")
         self.parts, self.comm, self.ops = parts, comm, ops or CudaOps()
         self.degree, self.ratio = int(degree), float(ratio)
+        self._programs, self._tail_out = {}, None
         dev = parts[0].vals.device
         world = comm.world
         offsets0 = parts[0].partition.offsets
@@ -727,9 +789,10 @@ class DistAMG:
             lam = math.sqrt(float(sq[0]))
         return lam
 
-    def _smooth(self, lv, cur, alt, b, zero_start):
+    def _smooth(self, lv, cur, alt, b, zero_start, comm=None):
         """Chebyshev(degree) on D^-1 A; returns the list of buffers holding the result (cur or alt)."""
-        ops, comm = self.ops, self.comm
+        ops = self.ops
+        comm = comm or self.comm
         lmax = 1.1 * lv['rho']
         lmin = lmax / self.ratio
         theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
@@ -752,18 +815,34 @@ class DistAMG:
                 cur, alt = alt, cur
         return cur, alt
 
+    def _host_step(self, fn):
+        """A step that is not a single kernel launch (halo exchange, all-gather, tail cycle): runs now, or is
+        deferred as a thunk while the cycle is being traced."""
+        rec = getattr(self.ops, 'record', None)
+        if rec is not None:
+            rec.append((fn, None, 'host step'))
+        else:
+            fn()
+
     def _cycle(self, l, b):
-        ops, comm = self.ops, self.comm
+        ops = self.ops
+        comm = _DeferredComm(self.comm, self._host_step)
         if l == self.lsw:
-            full = comm.allgather(b, self.offsets[l])
-            out = []
-            for part_idx, f in enumerate(full):
-                z = self.tail.precondition(f)
-                r = self.parts[part_idx].rank
-                out.append(z[self.offsets[l][r]:self.offsets[l][r + 1]])
-            return out
+            torch = L.require_cuda()
+            if self._tail_out is None:
+                self._tail_out = [torch.empty(self.offsets[l][p.rank + 1] - self.offsets[l][p.rank], dtype=torch.float64,
+                                              device=p.vals.device) for p in self.parts]
+
+            def tail_step(b=b, l=l):
+                full = self.comm.allgather(b, self.offsets[l])
+                for part_idx, f in enumerate(full):
+                    z = self.tail.precondition(f)
+                    r = self.parts[part_idx].rank
+                    self._tail_out[part_idx].copy_(z[self.offsets[l][r]:self.offsets[l][r + 1]])
+            self._host_step(tail_step)
+            return self._tail_out
         lv = self.levels[l]
-        cur, alt = self._smooth(lv, lv['xa'], lv['xb'], b, True)
+        cur, alt = self._smooth(lv, lv['xa'], lv['xb'], b, True, comm)
         comm.halo(lv['A'], cur)
         for a, x, bi, r in zip(lv['A'], cur, b, lv['r']):
             ops.spmv_axpy(a, x, bi, -1, r)                      # r[:nloc] = b - A x   (r is laid out for R's halo)
@@ -771,14 +850,36 @@ class DistAMG:
         for R, r, bc in zip(lv['R'], lv['r'], lv['bc']):
             ops.spmv(R, r, bc)
         xc = self._cycle(l + 1, lv['bc'])
-        for P, xce, x_c in zip(lv['P'], lv['xc'], xc):
-            xce[:P.ncol] = x_c
+
+        def fill_coarse(lv=lv, xc=xc):
+            for P, xce, x_c in zip(lv['P'], lv['xc'], xc):
+                xce[:P.ncol] = x_c
+        self._host_step(fill_coarse)
         comm.halo(lv['P'], lv['xc'])
         for P, xce, x in zip(lv['P'], lv['xc'], cur):
             ops.spmv_axpy(P, xce, x, +1, x)                     # x += P x_c (owned rows)
-        cur, alt = self._smooth(lv, cur, alt, b, False)
+        cur, alt = self._smooth(lv, cur, alt, b, False, comm)
         return [x[:a.nloc] for a, x in zip(lv['A'], cur)]
 
     def apply(self, r_list):
-        """z = M^-1 r (collective)."""
-        return self._cycle(0, r_list)
+        """z = M^-1 r (collective).  The cycle is traced once per set of input buffers into a list of
+        (kernel, prebuilt arguments) / host-step entries and replayed afterwards."""
+        if not hasattr(self.ops, 'record') or os.environ.get('MWX_DIST_REPLAY', '1') == '0':   # stand-in ops / A-B switch
+            return self._cycle(0, r_list)
+        key = tuple(r.data_ptr() for r in r_list)
+        if key not in self._programs:
+            self.ops.record = []
+            try:
+                out = self._cycle(0, r_list)
+                self._programs[key] = (self.ops.record, out, r_list)
+            finally:
+                self.ops.record = None
+        prog, out, _keep = self._programs[key]
+        for fn, args, what in prog:
+            if args is None:
+                fn()
+            else:
+                rc = fn(*args)
+                if rc:
+                    L.check(rc, what)
+        return out

@@ -61,6 +61,46 @@ class MeshTri:
                                          L.ptr(self.d_v2t_idx), L.ptr(fstart), self.nf,
                                          L.ptr(self.d_facets), L.ptr(self.d_t2f), st), 'mwx_mesh_facets_fill')
 
+    @classmethod
+    def _from_device(cls, d_pxy, d_t, nv, nt):
+        """Mesh from device arrays (pxy interleaved, t as [t0 | t1 | t2] int32); columns of t get sorted like the
+        public constructor does."""
+        self = cls.__new__(cls)
+        self.device = d_pxy.device
+        self.d_pxy, self.d_t, self.nv, self.nt = d_pxy.contiguous(), d_t.contiguous(), int(nv), int(nt)
+        L.check(L.lib().mwx_mesh_sort_columns(self.nt, L.ptr(self.d_t), L.stream()), 'mwx_mesh_sort_columns')
+        self._build_facets()
+        return self
+
+    def renumbered(self):
+        """The same mesh with vertices and elements renumbered along a Hilbert curve (no reference counterpart; the
+        reference's meshes keep the order red refinement produces).  Facet and DOF numbers then follow skfem's rules
+        on the renumbered arrays, so everything downstream is unchanged - but an element's vertices, edges and
+        neighbours now sit close together in memory, which is what the row-gather assembly and the SpMV's x-gathers
+        want.  ``vertex_order[i]`` / ``element_order[j]`` give the old number of new vertex i / new element j."""
+        torch = L.require_cuda()
+        lib, st = L.lib(), L.stream()
+        pxy = self.d_pxy.reshape(self.nv, 2)
+        lo = pxy.min(dim=0).values
+        ext = float((pxy.max(dim=0).values - lo).max().item()) or 1.0
+        x0, y0 = float(lo[0].item()), float(lo[1].item())
+        keys = torch.empty(self.nv, dtype=torch.int64, device=self.device)
+        L.check(lib.mwx_hilbert_keys(self.nv, L.ptr(self.d_pxy), x0, y0, ext, L.ptr(keys), st), 'mwx_hilbert_keys')
+        vorder = torch.argsort(keys, stable=True)
+        inv = torch.empty_like(vorder)
+        inv[vorder] = torch.arange(self.nv, dtype=torch.int64, device=self.device)
+        new_pxy = pxy[vorder].contiguous().reshape(-1)
+        t = self.d_t.reshape(3, self.nt).long()
+        cxy = (pxy[t[0]] + pxy[t[1]] + pxy[t[2]]) / 3.0
+        ckeys = torch.empty(self.nt, dtype=torch.int64, device=self.device)
+        cflat = cxy.contiguous().reshape(-1)
+        L.check(lib.mwx_hilbert_keys(self.nt, L.ptr(cflat), x0, y0, ext, L.ptr(ckeys), st), 'mwx_hilbert_keys')
+        eorder = torch.argsort(ckeys, stable=True)
+        new_t = inv[t[:, eorder]].to(torch.int32).contiguous().reshape(-1)
+        m = MeshTri._from_device(new_pxy, new_t, self.nv, self.nt)
+        m.vertex_order, m.element_order = vorder, eorder
+        return m
+
     def refine(self, times=1):
         """Uniform red refinement, in place like skfem's ``m.refine()``."""
         torch = L.require_cuda()

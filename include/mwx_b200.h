@@ -76,7 +76,9 @@ int mwx_pattern_count(int64_t ndofs, int64_t nt, int32_t ndpe, const int32_t *ed
                       const int32_t *r2e_idx, int64_t *indptr, int64_t *nnz_host,
                       int32_t *max_row_host, void *stream);
 /* Pass 2: indices (nnz, ascending per row) and the slot map: for pair p of r2e_idx (row r, element e)
- * slot8[8*p + j] = position of column edofs[j][e] inside row r (j < ndpe; other bytes unused).
+ * slot8[8*p + j] = position of column edofs[j][e] inside row r (j < ndpe <= 6).  Byte 7 is an accumulate mask:
+ * bit j set = an earlier pair of the same row already wrote that slot (this pair adds), clear = first touch (plain
+ * store) - mwx_assemble_morley relies on it to skip the zero-fill of its shared-memory row image; byte 6 unused.
  * ndpe = DOFs per element: 6 (Morley, P2) or 3 (P1). */
 int mwx_pattern_fill(int64_t ndofs, int64_t nt, int32_t ndpe, const int32_t *edofs, const int64_t *r2e_ptr,
                      const int32_t *r2e_idx, const int64_t *indptr, int32_t *indices,
@@ -274,6 +276,10 @@ int mwx_dist_rows_fill(int64_t nloc, const int32_t *rows, const int64_t *indptr,
 int mwx_dist_localize(int64_t nnz, const int32_t *cols_g, int32_t lo, int32_t hi, const int32_t *ghosts,
                       int32_t nghost, int32_t nloc, int32_t *cols_l, void *stream);
 int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *idx, double *dst, void *stream);
+/* Halo push over peer memory: dst[s][i - seg[s]] = v[idx[i]] for seg[s] <= i < seg[s+1]; dst[s] = the neighbour's
+ * ghost segment (a peer pointer), all arrays device-resident.  One launch per exchange whatever the neighbour count. */
+int mwx_halo_push(int64_t total, int32_t nseg, const int64_t *seg, const int32_t *idx, const double *v,
+                  double *const *dst, void *stream);
 
 /* CG building blocks chained by the multi-GPU driver between halo exchanges and all-reduces.  ws: zero-initialised
  * workspace of mwx_dcg_workspace_doubles() doubles; ws[0..4] = {rho, rho_prev, pq, rr, aux}.  Kernels leave LOCAL
