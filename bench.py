@@ -35,7 +35,8 @@ if ROOT not in sys.path:
 EPS = 1e-2            # eps^2 = 1e-4 (SURVEY 8d microbench setting)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the SAME
 # kernels on the level-12 workload (profiles/r01_ncu_final_spmv_assembly.txt); None for other levels.
-NCU_TRAFFIC_BYTES = {12: {'k_spmv': 10.374417e9 + 0.536002e9, 'k_assemble_morley': 12.214540e9 + 6.146322e9}}
+NCU_TRAFFIC_BYTES = {12: {'k_spmv': 10.374417e9 + 0.536002e9, 'k_assemble_morley': 12.228423e9 + 6.146362e9,
+                          'k_assemble_morley_renumbered': 7.890940e9 + 6.137720e9}}
 TOL = 1e-8            # the reference's tol (ref main/example1/run.py:20)
 
 
@@ -301,6 +302,26 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, rs_e2e = timed(True, args.steps, 1)
 
+    # the same assembly on the Hilbert-renumbered copy of the mesh (MeshTri.renumbered(): same triangles, vertex and
+    # element numbers follow a space-filling curve) - outside the timed steps, reported beside the default order
+    asm_renum_ms = None
+    if args.level <= 12:
+        gm2 = gm.renumbered()
+        basis2 = F.InteriorBasis(gm2, F.ElementTriMorley(), intorder=5)
+        K2r = F.asm_gpu(form, basis2)
+        for _ in range(3):
+            F.asm_gpu(form, basis2, out=K2r.d_data)
+        e0, e1 = ev(), ev()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            F.asm_gpu(form, basis2, out=K2r.d_data)
+        e1.record()
+        torch.cuda.synchronize()
+        asm_renum_ms = e0.elapsed_time(e1) / 5
+        del K2r, basis2, gm2
+        torch.cuda.empty_cache()
+
     # solution check of the last solve (manufactured x*)
     xerr = float(torch.linalg.norm(rs[-1]['x'] - xstar) / torch.linalg.norm(xstar))
 
@@ -346,10 +367,15 @@ def main():
                      'unit': 'GB/s', 'frac': spmv_gbs / peak,
                      'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_spmv'), 'peak_source': peak_src,
                      'algorithmic_bytes': spmv_bytes},
-        'roofline_assembly': {'kernel': 'k_assemble_morley', 'bound': 'hbm', 'achieved': asm_gbs, 'peak': peak,
-                              'unit': 'GB/s', 'frac': asm_gbs / peak,
+        'roofline_assembly': {'kernel': 'k_element_geometry + k_assemble_morley_persistent', 'bound': 'hbm', 'achieved': asm_gbs,
+                              'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                               'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_assemble_morley'),
-                              'algorithmic_bytes': asm_bytes},
+                              'algorithmic_bytes': asm_bytes,
+                              'renumbered_mesh': None if asm_renum_ms is None else {
+                                  'ms': asm_renum_ms, 'mdof_s': N / (asm_renum_ms * 1e-3) / 1e6,
+                                  'achieved': asm_bytes / (asm_renum_ms * 1e-3) / 1e9,
+                                  'frac': asm_bytes / (asm_renum_ms * 1e-3) / 1e9 / peak,
+                                  'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_assemble_morley_renumbered')}},
         'e2e': {'value': units / (e2e_ms / args.steps * 1e-3) / 1e6, 'unit': 'MDOF/s',
                 'h2d_bytes_per_step': int(p_host.numel() * 8 + t_host.numel() * 4 + b_host.numel() * 8),
                 'd2h_bytes_per_step': int(x_host.numel() * 8), 'ms_per_step': e2e_ms / args.steps},
@@ -395,11 +421,35 @@ def run_microbench(args, torch, F):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        rows.append({'level': level, 'squares': f'{2 ** level}x{2 ** level}', 'dofs': basis.N, 'triangles': gm.nt,
-                     'nnz': pat['nnz'], 'assembly_ms': ms, 'mdof_s': basis.N / ms / 1e3,
-                     'gbs_algorithmic_308B_per_element': 308 * gm.nt / ms / 1e6,
-                     'frac_of_peak': 308 * gm.nt / ms / 1e6 / peak, 'setup_s_mesh_pattern': t_setup})
-        del K, basis, gm, pat
+        row = {'level': level, 'squares': f'{2 ** level}x{2 ** level}', 'dofs': basis.N, 'triangles': gm.nt,
+               'nnz': pat['nnz'], 'assembly_ms': ms, 'mdof_s': basis.N / ms / 1e3,
+               'gbs_algorithmic_308B_per_element': 308 * gm.nt / ms / 1e6,
+               'frac_of_peak': 308 * gm.nt / ms / 1e6 / peak, 'setup_s_mesh_pattern': t_setup}
+        del K, basis, pat
+        torch.cuda.empty_cache()
+        # same triangles, Hilbert-renumbered vertices / elements (MeshTri.renumbered())
+        t0 = time.perf_counter()
+        gm2 = gm.renumbered()
+        del gm
+        basis = F.InteriorBasis(gm2, F.ElementTriMorley())
+        basis.pattern()
+        torch.cuda.synchronize()
+        t_setup2 = time.perf_counter() - t0
+        K = F.asm_gpu(form, basis)
+        for _ in range(max(args.warmup, 3)):
+            F.asm_gpu(form, basis, out=K.d_data)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            F.asm_gpu(form, basis, out=K.d_data)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / args.steps
+        row['renumbered_mesh'] = {'assembly_ms': ms2, 'mdof_s': basis.N / ms2 / 1e3,
+                                  'gbs_algorithmic_308B_per_element': 308 * gm2.nt / ms2 / 1e6,
+                                  'frac_of_peak': 308 * gm2.nt / ms2 / 1e6 / peak, 'setup_s_renumber_pattern': t_setup2}
+        rows.append(row)
+        del K, basis, gm2
         torch.cuda.empty_cache()
     print(json.dumps({'metric': 'assembly_MDOF_per_s', 'unit': 'MDOF/s', 'value': rows[1]['mdof_s'], 'n_gpus': 1,
                       'steps': args.steps, 'warmup': max(args.warmup, 3), 'dtype': 'f64', 'data': 'synthetic',

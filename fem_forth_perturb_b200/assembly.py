@@ -191,13 +191,15 @@ def asm_load(form, basis):
     return out.cpu().numpy()
 
 
-def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
+def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
     """Assemble ``form`` on ``ubasis`` -> :class:`DeviceCSR` (``.tocsr()`` gives scipy's matrix).
 
     ``form``: a descriptor from :mod:`forms` (or a linear combination such as
     ``eps**2 * a_load + b_load`` - one fused kernel pass), or an object named like the reference's forms.
     ``sigma``: the module-level ``sigma`` that ``penalty_3`` closes over (ref main/example1/run.py:27,146).
     Facet forms are returned on the INTERIOR pattern so that ``eps**2*A + eps**2*P + B`` is a device axpby.
+    ``out`` / ``accumulate``: write the values into an existing nnz-sized device vector, or add to it (Morley
+    interior forms; the penalty forms always add into ``out``).
     """
     torch = L.require_cuda()
     from .forms import LinearFormGPU
@@ -262,8 +264,8 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None):
     vals = out if out is not None else torch.empty(pat['nnz'], dtype=torch.float64, device=m.device)
     L.check(lib.mwx_assemble_morley(ubasis.N, m.nt, L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(pat['exy']), 1,
                                     L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']),
-                                    L.ptr(pat['indptr']), f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0), 0,
-                                    L.ptr(vals), st),
+                                    L.ptr(pat['indptr']), f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0),
+                                    1 if (accumulate and out is not None) else 0, L.ptr(vals), st),
             'mwx_assemble_morley')
     return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
 

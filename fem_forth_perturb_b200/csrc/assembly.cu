@@ -16,6 +16,7 @@
 // Algorithmic bytes per element (the figure bench.py's roofline uses):
 //   read  incidence codes 6*4 = 24, slot map 6*8 = 48, t 12, coordinates ~8, indptr+r2e_ptr ~32
 //   write CSR values 23*8 = 184                                                   => 308 B/element
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -313,21 +314,28 @@ __global__ void __launch_bounds__(ASM_ROWS, 6) k_assemble_morley(
 
 // ---- whole-matrix assembly: persistent, software-pipelined form of the kernel above ---------------------------
 // The row kernel above is bound by a CHAIN of dependent DRAM latencies per CTA (tile bounds -> pair words ->
-// first record -> ... ; ncu: 55 % of warp time on long_scoreboard, DRAM 36 %, L1 74 %) rather than by bytes.
+// first record -> ... ; ncu: 55 % of warp time on long_scoreboard, DRAM 36 %) rather than by bytes.
 // Here CTAs are persistent (occupancy x 148) and stride over the 128-row tiles with everything a tile needs
-// fetched one tile ahead, asynchronously:
+// fetched one tile ahead, asynchronously, into the other of two shared-memory stages:
 //   * the tile's pair words (incidence codes + slot words: one contiguous range each) by two TMA bulk copies
 //     issued by one thread (mbarrier complete_tx), their range bounds loaded one further tile ahead;
 //   * its row pointers (r2e_ptr, indptr segments) by per-thread 8-byte cp.async;
 //   * and inside a tile each thread keeps TWO geometry records in flight.
+// After that the kernel sits on the L1/shared-memory data pipe (74 %): every scattered 32-byte record sector and
+// every conflicting row-image update costs a full wavefront.  Measured and rejected on top of this form (level 12,
+// all within -8 .. +1 %): a three-stage ring with L2 prefetch of the next tile's records, streaming the previous
+// tile out while the first records arrive, LDS-only addressing of the pair words, 5 CTAs/SM at 96 registers.
+constexpr int ASMP_PAIRS = 800;                  // pair words staged per tile (768 = a tile of interior vertices)
+constexpr int ASMP_CAP = ASM_ROWS * 20;          // shared-memory row image (2432 = a tile of interior vertices)
 struct AsmStage {
-    unsigned long long slot[ASM_PAIRS + 2];      // staged from an even pair index (16-byte aligned source)
-    int32_t code[ASM_PAIRS + 8];                 // staged from a multiple-of-4 pair index
+    unsigned long long slot[ASMP_PAIRS + 2];     // staged from an even pair index (16-byte aligned source)
+    int32_t code[ASMP_PAIRS + 8];                // staged from a multiple-of-4 pair index
     int64_t rptr[ASM_ROWS + 2];                  // r2e_ptr[i0 .. i1]
     int64_t optr[ASM_ROWS + 2];                  // indptr[i0 .. i1]
 };
 static_assert(sizeof(AsmStage) % 16 == 0, "stage must keep 16-byte alignment");
-constexpr int ASMP_SMEM_BYTES = ASM_CAP * 8 + 2 * (int)sizeof(AsmStage) + 64;
+static_assert(offsetof(AsmStage, code) % 16 == 0, "TMA destination alignment");
+constexpr int ASMP_SMEM_BYTES = ASMP_CAP * 8 + 2 * (int)sizeof(AsmStage) + 64;
 
 __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
     int64_t nrows, const double2 *__restrict__ exy, const int64_t *__restrict__ r2e_ptr,
@@ -336,8 +344,8 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
     int tma_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *acc = reinterpret_cast<double *>(smem_raw);
-    AsmStage *stg = reinterpret_cast<AsmStage *>(smem_raw + ASM_CAP * 8);
-    unsigned char *tail = smem_raw + ASM_CAP * 8 + 2 * sizeof(AsmStage);
+    AsmStage *stg = reinterpret_cast<AsmStage *>(smem_raw + ASMP_CAP * 8);
+    unsigned char *tail = smem_raw + ASMP_CAP * 8 + 2 * sizeof(AsmStage);
     uint64_t *bar = reinterpret_cast<uint64_t *>(tail);                  // [2]
     int64_t *s_cb0 = reinterpret_cast<int64_t *>(tail + 16);            // [2] first staged code index
     int64_t *s_sb0 = reinterpret_cast<int64_t *>(tail + 32);            // [2] first staged slot-word index
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
 
     const int tid = threadIdx.x;
     const int64_t ntiles = (nrows + ASM_ROWS - 1) / ASM_ROWS;
+    const int64_t G = gridDim.x;
     int64_t npairs = 0;
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
     auto issue = [&](int64_t pb0, int64_t pb1, int stage) {              // thread 0
         const int64_t cb0 = pb0 & ~(int64_t)3, ce = (pb1 + 3) & ~(int64_t)3;
         const int64_t sb0 = pb0 & ~(int64_t)1, se = (pb1 + 1) & ~(int64_t)1;
-        if (tma_ok && pb1 > pb0 && pb1 - pb0 <= ASM_PAIRS && ce <= npairs && se <= npairs) {
+        if (tma_ok && pb1 > pb0 && pb1 - pb0 <= ASMP_PAIRS && ce <= npairs && se <= npairs) {
             s_cb0[stage] = cb0;
             s_sb0[stage] = sb0;
             s_flat[stage] = 1;
@@ -393,20 +402,20 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
         if (tid == 0) {
             bounds(tile, nb0, nb1);
             issue(nb0, nb1, 0);
-            if (tile + gridDim.x < ntiles) bounds(tile + gridDim.x, nb0, nb1);
+            if (tile + G < ntiles) bounds(tile + G, nb0, nb1);
         }
         fetch_ptrs(tile, 0);
     }
     cp_async_wait_all();
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
-    for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+    for (int k = 0; tile < ntiles; tile += G, ++k) {
         const int stage = k & 1;
-        const int64_t next = tile + gridDim.x;
+        const int64_t next = tile + G;
         if (next < ntiles) {
             if (tid == 0) {
                 issue(nb0, nb1, stage ^ 1);
-                if (next + gridDim.x < ntiles) bounds(next + gridDim.x, nb0, nb1);     // lands during this tile
+                if (next + G < ntiles) bounds(next + G, nb0, nb1);       // lands during this tile
             }
             fetch_ptrs(next, stage ^ 1);
         }
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
         const int nr = (int)(i0 + ASM_ROWS < nrows ? ASM_ROWS : nrows - i0);
         const int64_t s0 = S.optr[0];
         const int64_t len = S.optr[nr] - s0;
-        const bool staged = len <= ASM_CAP;          // CTA-uniform
+        const bool staged = len <= ASMP_CAP;         // CTA-uniform
         const bool flat = s_flat[stage] != 0;        // CTA-uniform
         if (flat) {
             if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
@@ -425,6 +434,7 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
             const int64_t pb = S.rptr[tid];
             const int np = (int)(S.rptr[tid + 1] - pb);
             const int64_t rs = S.optr[tid];
+            // one (generic) pointer each: shared-memory stage, or the global arrays for an oversized tile
             const int32_t *codes = flat ? S.code + (pb - s_cb0[stage]) : r2e_idx + pb;
             const unsigned long long *slots = flat ? S.slot + (pb - s_sb0[stage]) : slot8 + pb;
             if (!staged && !accumulate) {
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(ASM_ROWS) k_assemble_morley_persistent(
                 for (int kk = tid; kk < (int)len; kk += ASM_ROWS) values[s0 + kk] = acc[kk];
         }
         cp_async_wait_all();             // next tile's row pointers have landed
-        __syncthreads();                 // stage and acc fully consumed before they are refilled
+        __syncthreads();                 // stage and row image fully consumed before they are refilled
     }
 }
 

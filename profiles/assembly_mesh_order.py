@@ -1,5 +1,5 @@
-import sys, time, torch, numpy as np
-sys.path.insert(0, '.')
+import os, sys, time, torch, numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import fem_forth_perturb_b200 as F
 from fem_forth_perturb_b200 import _lib as L
 lvl = int(sys.argv[1]) if len(sys.argv) > 1 else 11

@@ -105,6 +105,41 @@ def test_values_against_well_conditioned_oracle(cuda, level):
     assert abs(A - A_ref).max() <= 1e-10 * abs(A_ref).max()
 
 
+def test_renumbered_mesh_is_the_same_mesh_and_assembles_bit_compatibly(cuda):
+    """MeshTri.renumbered(): a vertex/element permutation of the same mesh; skfem's numbering rules applied to the
+    permuted arrays (oracle built from the same p, t) give the same facets, pattern and values."""
+    import fem_forth_perturb_b200 as F
+    gm0 = F.MeshTri.init_lshaped().refine(4)
+    gm = gm0.renumbered()
+    vo, eo = gm.vertex_order.cpu().numpy(), gm.element_order.cpu().numpy()
+    assert np.array_equal(np.sort(vo), np.arange(gm0.nv)) and np.array_equal(np.sort(eo), np.arange(gm0.nt))
+    assert np.array_equal(gm.p, gm0.p[:, vo])
+    assert np.array_equal(np.sort(vo[gm.t], axis=0), np.sort(gm0.t[:, eo], axis=0))      # same triangles
+    om = OMesh(gm.p, gm.t)
+    assert np.array_equal(gm.t, om.t) and np.array_equal(gm.facets, om.facets) and np.array_equal(gm.t2f, om.t2f)
+    K_or = pl.assemble_K2(OInterior(om, 'Morley', 5, shift=True), 0.1)
+    K = F.asm_gpu(0.01 * F.a_load + F.b_load, F.InteriorBasis(gm, F.ElementTriMorley())).tocsr()
+    assert np.array_equal(K.indptr, K_or.indptr) and np.array_equal(K.indices, K_or.indices)
+    assert _relmax(K, K_or) < 1e-12
+    # locality: neighbouring vertices of an element are close in the new numbering
+    assert np.median(np.ptp(gm.t, axis=0)) < np.median(np.ptp(gm0.t, axis=0))
+
+
+def test_assembly_accumulate_and_repeatability(cuda):
+    """values += (accumulate path) and bit-reproducibility of the persistent row kernel."""
+    import fem_forth_perturb_b200 as F
+    gm = F.MeshTri().refine(6)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    K1 = F.asm_gpu(0.25 * F.a_load + F.b_load, basis)
+    K2 = F.asm_gpu(0.25 * F.a_load + F.b_load, basis)
+    assert bool((K1.d_data == K2.d_data).all())                    # no atomics: identical bits run to run
+    Ksum = (0.25 * F.asm_gpu(F.a_load, basis) + F.asm_gpu(F.b_load, basis)).tocsr()
+    assert _relmax(Ksum, K1.tocsr()) < 1e-14
+    Kacc = F.asm_gpu(0.25 * F.a_load, basis)
+    F.asm_gpu(F.b_load, basis, out=Kacc.d_data, accumulate=True)
+    assert _relmax(Kacc.tocsr(), K1.tocsr()) < 1e-14
+
+
 def test_generic_triangles_lshape(cuda):
     """Non-right, differently oriented triangles: perturbed L-shape mesh."""
     import fem_forth_perturb_b200 as F
