@@ -33,6 +33,18 @@ def _to_device_vec(b, device):
     return b.to(device=device, dtype=torch.float64).contiguous()
 
 
+def _gather_values(src, idx, out):
+    """out[k] = src[idx[k]] on the device (idx int32 or int64)."""
+    fn = L.lib().mwx_gather_f64 if idx.dtype == L.require_cuda().int32 else L.lib().mwx_gather_f64_i64
+    L.check(fn(idx.numel(), L.ptr(src), L.ptr(idx), L.ptr(out), L.stream()), 'mwx_gather_f64')
+    return out
+
+
+def _index_dtype(nnz):
+    torch = L.require_cuda()
+    return torch.int32 if nnz < 2 ** 31 else torch.int64
+
+
 class Reordering:
     """Hilbert-curve renumbering of a system (internal to the throughput solvers; results are permuted back).
 
@@ -53,6 +65,7 @@ class Reordering:
         self.iperm = torch.empty(n, dtype=torch.int32, device=xy.device)
         self.iperm[order] = torch.arange(n, dtype=torch.int32, device=xy.device)
         self.n = n
+        self._patterns = {}                 # (pattern key, nnz) -> permuted pattern + value map, see matrix()
 
     @classmethod
     def for_matrix(cls, A):
@@ -60,9 +73,33 @@ class Reordering:
             return None
         return cls(A.coords())
 
-    def matrix(self, A, out=None):
+    def matrix(self, A, out=None, scratch=False):
+        """P A P^T as a DeviceCSR.  The first call for a sparsity pattern runs the full permutation
+        (``mwx_csr_permute``: rows gathered, columns renumbered and re-sorted); from the second call on the
+        permuted pattern is reused and only the values move, through a cached source-index map (one gather
+        pass, ~20x cheaper).  ``out`` = (indptr, indices, values) buffers to fill; ``scratch=True`` returns the
+        values in a buffer owned by this object (overwritten by the next scratch call)."""
         torch = L.require_cuda()
         dev = A.d_data.device
+        key = (A.pattern_key, A.nnz)
+        ent = self._patterns.get(key)
+        if ent is not None:
+            if ent['vmap'] is None:                                     # second use: pay for the map once
+                ids = torch.arange(A.nnz, dtype=torch.float64, device=dev)
+                tmp = torch.empty(A.nnz, dtype=torch.float64, device=dev)
+                L.check(L.lib().mwx_csr_permute(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(ids),
+                                                L.ptr(self.perm), L.ptr(self.iperm), L.ptr(ent['indptr']),
+                                                L.ptr(ent['indices']), L.ptr(tmp), L.stream()), 'mwx_csr_permute')
+                ent['vmap'] = tmp.to(_index_dtype(A.nnz))
+                del ids, tmp
+            if scratch:
+                if ent['scratch'] is None:
+                    ent['scratch'] = torch.empty(A.nnz, dtype=torch.float64, device=dev)
+                vals = ent['scratch']
+            else:
+                vals = out[2] if out is not None else torch.empty(A.nnz, dtype=torch.float64, device=dev)
+            _gather_values(A.d_data, ent['vmap'], vals)
+            return DeviceCSR(ent['indptr'], ent['indices'], vals, A.shape)
         if out is None:
             out = (torch.empty(self.n + 1, dtype=torch.int64, device=dev),
                    torch.empty(A.nnz, dtype=torch.int32, device=dev),
@@ -70,6 +107,9 @@ class Reordering:
         L.check(L.lib().mwx_csr_permute(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data),
                                         L.ptr(self.perm), L.ptr(self.iperm), L.ptr(out[0]), L.ptr(out[1]),
                                         L.ptr(out[2]), L.stream()), 'mwx_csr_permute')
+        # keep the pattern tensors of the source alive with the entry: the key is made of their addresses
+        self._patterns[key] = dict(indptr=out[0].clone(), indices=out[1].clone(), vmap=None, scratch=None,
+                                   source=(A.d_indptr, A.d_indices))
         return DeviceCSR(out[0], out[1], out[2], A.shape)
 
     def _gather(self, v, idx):
@@ -199,7 +239,7 @@ def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=No
     bd = _to_device_vec(b, dev)
     ro = reordering if reordering is not None else (amg.reordering if amg is not None else None)
     if ro is not None:
-        A = ro.matrix(A)
+        A = ro.matrix(A, scratch=True)
         bd = ro.forward(bd)
     x = torch.empty(n, dtype=torch.float64, device=dev)
     work = torch.empty(4 * n, dtype=torch.float64, device=dev)
@@ -422,6 +462,7 @@ class CondensePlan:
         self.n_out, self.nnz_out = int(n_out.value), int(nnz_out.value)
         self.indptr_out = indptr_out[:self.n_out + 1].clone()
         self.indices_out = torch.empty(self.nnz_out, dtype=torch.int32, device=dev)
+        self._matrix_applies, self._vmap = 0, None      # matrix-only applies: values move through a cached map
 
     def apply(self, A, b=None, x=None, values_out=None):
         """-> (Aout DeviceCSR, bout or None); b/x may be numpy or device tensors."""
@@ -432,6 +473,23 @@ class CondensePlan:
         dev = A.d_data.device
         vals = values_out if values_out is not None else torch.empty(self.nnz_out, dtype=torch.float64, device=dev)
         have_b = b is not None
+        if not have_b:
+            # Matrix only (re-assembly on the same mesh, eps sweep): from the second time on just gather the kept
+            # values through a source-index map instead of re-walking the pattern.
+            self._matrix_applies += 1
+            if self._matrix_applies >= 2 and self._vmap is None:
+                ids = torch.arange(A.nnz, dtype=torch.float64, device=dev)
+                tmp = torch.empty(self.nnz_out, dtype=torch.float64, device=dev)
+                L.check(L.lib().mwx_condense_fill(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(ids),
+                                                  L.ptr(self.keep), L.ptr(self.newid), L.ptr(self.indptr_out),
+                                                  L.ptr(self.indices_out), L.ptr(tmp), None, None, None,
+                                                  L.stream()), 'mwx_condense_fill')
+                self._vmap = tmp.to(_index_dtype(A.nnz))
+                del ids, tmp
+            if self._vmap is not None:
+                _gather_values(A.d_data, self._vmap, vals)
+                return DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out),
+                                 coords=self._coords_of(A, dev)), None
         bd = _to_device_vec(b, dev) if have_b else None
         xd = _to_device_vec(x, dev) if (have_b and x is not None) else None
         b_out = torch.empty(self.n_out, dtype=torch.float64, device=dev) if have_b else None
@@ -439,16 +497,21 @@ class CondensePlan:
                                           L.ptr(self.keep), L.ptr(self.newid), L.ptr(self.indptr_out),
                                           L.ptr(self.indices_out), L.ptr(vals), L.ptr(bd), L.ptr(xd), L.ptr(b_out),
                                           L.stream()), 'mwx_condense_fill')
-        coords = None
-        if getattr(A, 'coords', None) is not None:
-            src, plan = A.coords, self
-
-            def coords():
-                if plan._I_dev is None:
-                    plan._I_dev = torch.from_numpy(np.ascontiguousarray(plan.I, dtype=np.int64)).to(dev)
-                return src()[plan._I_dev]
-        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out), coords=coords)
+        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out),
+                         coords=self._coords_of(A, dev))
         return Aout, b_out
+
+    def _coords_of(self, A, dev):
+        if getattr(A, 'coords', None) is None:
+            return None
+        torch = L.require_cuda()
+        src, plan = A.coords, self
+
+        def coords():
+            if plan._I_dev is None:
+                plan._I_dev = torch.from_numpy(np.ascontiguousarray(plan.I, dtype=np.int64)).to(dev)
+            return src()[plan._I_dev]
+        return coords
 
 
 def condense(A, b=None, x=None, I=None, D=None, expand=True):

@@ -109,7 +109,12 @@ def test_renumbered_mesh_is_the_same_mesh_and_assembles_bit_compatibly(cuda):
     """MeshTri.renumbered(): a vertex/element permutation of the same mesh; skfem's numbering rules applied to the
     permuted arrays (oracle built from the same p, t) give the same facets, pattern and values."""
     import fem_forth_perturb_b200 as F
-    gm0 = F.MeshTri.init_lshaped().refine(4)
+    om0 = OMesh.init_lshaped().refine(4)
+    rng = np.random.default_rng(3)
+    inner = np.setdiff1d(np.arange(om0.nv), om0.boundary_nodes())
+    p0 = om0.p.copy()
+    p0[:, inner] += 0.004 * rng.standard_normal((2, len(inner)))   # generic triangles: no exactly-zero entries that
+    gm0 = F.MeshTri(p0, om0.t)                                      # skfem's eliminate_zeros() would drop
     gm = gm0.renumbered()
     vo, eo = gm.vertex_order.cpu().numpy(), gm.element_order.cpu().numpy()
     assert np.array_equal(np.sort(vo), np.arange(gm0.nv)) and np.array_equal(np.sort(eo), np.arange(gm0.nt))
@@ -421,6 +426,21 @@ def test_locality_reordering_is_a_similarity_transform(cuda):
     ref = Ks[perm][:, perm].tocsr(); ref.sort_indices()
     assert np.array_equal(Kp.indptr, ref.indptr) and np.array_equal(Kp.indices, ref.indices)
     assert np.array_equal(Kp.data, ref.data)                      # pure data movement: bit-exact
+    # later calls on the same pattern reuse the permuted pattern and only gather the values (cached source map)
+    Kc2 = 2.0 * Kc
+    for scratch in (False, True, False):
+        Kp2 = ro.matrix(Kc2, scratch=scratch).tocsr()
+        assert np.array_equal(Kp2.indptr, ref.indptr) and np.array_equal(Kp2.indices, ref.indices)
+        assert np.array_equal(Kp2.data, 2.0 * ref.data)
+    # ... and a CondensePlan applied repeatedly to re-assembled matrices does the same
+    plan = F.CondensePlan(K, D=D)
+    for scale in (1.0, 3.0, 0.5):
+        Kci, none = plan.apply(scale * K)
+        Kci = Kci.tocsr()
+        assert none is None and np.array_equal(Kci.indptr, Ks.indptr) and np.array_equal(Kci.indices, Ks.indices)
+        assert np.array_equal(Kci.data, scale * Ks.data)
+    Kcb, bcb = plan.apply(K, f, np.zeros(K.shape[0]))             # with a load vector: the full pass
+    assert np.array_equal(Kcb.tocsr().data, Ks.data) and np.allclose(bcb.cpu().numpy(), bc, rtol=0, atol=0)
     # locality: consecutive DOFs along the curve are geometric neighbours (mean jump ~ h, not ~ 1)
     xy = Kc.coords().cpu().numpy()[perm]
     jump = np.linalg.norm(np.diff(xy, axis=0), axis=1)
