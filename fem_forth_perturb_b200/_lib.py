@@ -65,11 +65,15 @@ _SIGNATURES = {
     'mwx_csr_diagonal': [i64, vp, vp, vp, vp, vp],
     'mwx_pcg_jacobi': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp],
     'mwx_amg_setup_host': [i64, vp, vp, vp, f64, i32, i32, ctypes.POINTER(vp)],
+    'mwx_amg_setup_sa_host': [i64, vp, vp, vp, vp, i32, i32, i32, f64, i32, i32, ctypes.POINTER(vp)],
+    'mwx_amg_level_candidates': [vp, i32, vp, vp],
     'mwx_amg_num_levels': [vp],
     'mwx_set_host_threads': [i32],
     'mwx_amg_level_dims': [vp, i32, i32, vp],
     'mwx_amg_level_copy': [vp, i32, i32, vp, vp, vp],
+    'mwx_amg_level_view': [vp, i32, i32, vp, vp, vp],
     'mwx_amg_level_splitting': [vp, i32, vp],
+    'mwx_amg_level_roots': [vp, i32, vp, vp],
     'mwx_amg_destroy_host': [vp],
     'mwx_gs_wavefronts_host': [i64, vp, vp, vp, vp, _pi64],
     'mwx_gs_wavefronts_backward_host': [i64, vp, vp, vp, vp, _pi64],

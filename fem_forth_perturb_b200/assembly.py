@@ -17,11 +17,12 @@ from .forms import as_form
 class DeviceCSR:
     """CSR matrix resident in HBM (int64 indptr, int32 indices, fp64 data); scipy-compatible view."""
 
-    def __init__(self, indptr, indices, data, shape, pattern_key=None, coords=None):
+    def __init__(self, indptr, indices, data, shape, pattern_key=None, coords=None, candidates=None):
         self.d_indptr, self.d_indices, self.d_data = indptr, indices, data
         self.shape = tuple(int(s) for s in shape)
         self.pattern_key = pattern_key if pattern_key is not None else (indptr.data_ptr(), indices.data_ptr())
         self.coords = coords          # optional callable -> device (n, 2) DOF locations (locality key)
+        self.candidates = candidates  # optional callable -> device (n, k) near-nullspace vectors (smoothed aggregation)
         self._spmv_plan = None
 
     def spmv_hint(self):
@@ -81,7 +82,7 @@ class DeviceCSR:
         b = other.d_data if other is not None else self.d_data
         L.check(L.lib().mwx_axpby(self.nnz, float(alpha), L.ptr(self.d_data), float(beta), L.ptr(b), L.ptr(out),
                                   L.stream()), 'mwx_axpby')
-        return DeviceCSR(self.d_indptr, self.d_indices, out, self.shape, self.pattern_key, self.coords)
+        return DeviceCSR(self.d_indptr, self.d_indices, out, self.shape, self.pattern_key, self.coords, self.candidates)
 
     def __mul__(self, c):
         if np.isscalar(c):
@@ -130,7 +131,7 @@ class DeviceCSR:
         csum = torch.zeros(self.nnz + 1, dtype=torch.int64, device=self.d_data.device)
         csum[1:] = torch.cumsum(mask.to(torch.int64), 0)
         return DeviceCSR(csum[self.d_indptr].contiguous(), self.d_indices[mask].contiguous(),
-                         self.d_data[mask].contiguous(), self.shape, coords=self.coords)
+                         self.d_data[mask].contiguous(), self.shape, coords=self.coords, candidates=self.candidates)
 
     @classmethod
     def from_scipy(cls, A, device=None):
@@ -224,7 +225,8 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
                                              L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']),
                                              L.ptr(pat['slot8']), L.ptr(pat['indptr']), L.ptr(vals), st),
                 'mwx_assemble_morley_mass')
-        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
+        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords,
+                      candidates=ubasis.nullspace_candidates)
         return K if f.terms['mass'] == 1.0 else f.terms['mass'] * K
     if f.kind == 'lagrange':
         if isinstance(ubasis.elem, ElementTriMorley):
@@ -254,7 +256,8 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
                                          L.ptr(pat['indices']), t.get('penalty_1', 0.0), t.get('penalty_2', 0.0),
                                          t.get('penalty_3', 0.0), float(sigma), L.ptr(vals), st),
                 'mwx_assemble_penalty')
-        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ib.N, ib.N), coords=ib.dof_coords)
+        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ib.N, ib.N), coords=ib.dof_coords,
+                         candidates=ib.nullspace_candidates)
     if not isinstance(ubasis, InteriorBasis):
         raise TypeError("asm_gpu expects an InteriorBasis or FacetBasis of this package")
     if f.kind != 'interior':
@@ -267,7 +270,8 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
                                     L.ptr(pat['indptr']), f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0),
                                     1 if (accumulate and out is not None) else 0, L.ptr(vals), st),
             'mwx_assemble_morley')
-    return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
+    return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords,
+                     candidates=ubasis.nullspace_candidates)
 
 
 asm = asm_gpu

@@ -132,6 +132,30 @@ class InteriorBasis:
                 self._coords = pxy.contiguous()
         return self._coords
 
+    def nullspace_candidates(self):
+        """Device (N, 3) fp64: the interpolants of 1, x, y in this basis - the near-nullspace of the stiffness
+        eps^2 (hess:hess) + (grad.grad) that smoothed aggregation is built on.  Morley: vertex DOFs (1, x, y),
+        facet DOFs (0, n_x, n_y) with the facet normal n = (d_y, -d_x)/|d|, d = p[f1] - p[f0] (skfem's
+        orientation: hess:hess annihilates these vectors to round-off).  Lagrange bases: nodal values."""
+        if getattr(self, '_candidates', None) is None:
+            torch = L.require_cuda()
+            m = self.mesh
+            pxy = m.d_pxy.reshape(m.nv, 2)
+            ones = torch.ones(m.nv, 1, dtype=torch.float64, device=m.device)
+            B = torch.cat((ones, pxy), dim=1)
+            if self.elem.facet_dofs:
+                f = m.d_facets.reshape(2, m.nf).long()
+                if isinstance(self.elem, ElementTriMorley):
+                    d = pxy[f[1]] - pxy[f[0]]
+                    ln = torch.sqrt((d * d).sum(dim=1))
+                    Bf = torch.stack((torch.zeros_like(ln), d[:, 1] / ln, -d[:, 0] / ln), dim=1)
+                else:                                    # P2: facet DOF = value at the midpoint
+                    mid = 0.5 * (pxy[f[0]] + pxy[f[1]])
+                    Bf = torch.cat((torch.ones(m.nf, 1, dtype=torch.float64, device=m.device), mid), dim=1)
+                B = torch.cat((B, Bf), dim=0)
+            self._candidates = B.contiguous()
+        return self._candidates
+
     # -- boundary DOFs -----------------------------------------------------------------------------
     def find_dofs(self, facets=None):
         """``basis.find_dofs()`` -> {'all': DofsView of the boundary}; with a dict of facet sets,

@@ -111,16 +111,19 @@ int upload_csr(const mwx_amg_host_t *h, int level, int which, DCsr &out, cudaStr
     int64_t dims[3];
     int rc = mwx_amg_level_dims(h, level, which, dims);
     if (rc) return rc;
-    std::vector<int64_t> ptr((size_t)dims[0] + 1);
-    std::vector<int32_t> idx((size_t)dims[2]);
-    std::vector<double> val((size_t)dims[2]);
-    rc = mwx_amg_level_copy(h, level, which, ptr.data(), idx.data(), val.data());
-    if (rc) return rc;
+    const int64_t *ptr = nullptr;
+    const int32_t *idx = nullptr;
+    const double *val = nullptr;
+    if ((rc = mwx_amg_level_view(h, level, which, &ptr, &idx, &val))) return rc;      // straight from the hierarchy
     out.rows = dims[0]; out.cols = dims[1]; out.nnz = dims[2];
-    if ((rc = upload(ptr, &out.ptr, st))) return rc;
-    if ((rc = upload(idx, &out.idx, st))) return rc;
-    if ((rc = upload(val, &out.val, st))) return rc;
-    MWX_CUDA(cudaStreamSynchronize(st));       // host staging vectors go out of scope
+    const size_t nnz = (size_t)dims[2];
+    if (cudaMalloc((void **)&out.ptr, sizeof(int64_t) * ((size_t)dims[0] + 1)) != cudaSuccess ||
+        cudaMalloc((void **)&out.idx, sizeof(int32_t) * (nnz ? nnz : 1)) != cudaSuccess ||
+        cudaMalloc((void **)&out.val, sizeof(double) * (nnz ? nnz : 1)) != cudaSuccess)
+        return MWX_E_NOMEM;
+    MWX_CUDA(cudaMemcpyAsync(out.ptr, ptr, sizeof(int64_t) * ((size_t)dims[0] + 1), cudaMemcpyHostToDevice, st));
+    MWX_CUDA(cudaMemcpyAsync(out.idx, idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
+    MWX_CUDA(cudaMemcpyAsync(out.val, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
     int tile_rows = 0;
     if ((rc = spmv_plan_rows(out.rows, out.ptr, &tile_rows, st))) return rc;
     out.plan = -(int64_t)tile_rows;

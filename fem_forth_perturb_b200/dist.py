@@ -673,11 +673,13 @@ class DistAMG:
 
     def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=500000,
                  max_levels=10, ops=None):
+        """mode 'chebyshev': the reference's Ruge-Stueben hierarchy; 'sa': smoothed aggregation (the global matrix
+        must carry near-nullspace candidates, see AMGHierarchy).  Chebyshev smoothing either way."""
         torch = L.require_cuda()
         from .solvers import AMGHierarchy
         from .assembly import DeviceCSR
-        if mode != 'chebyshev':
-            raise NotImplementedError("the partitioned V-cycle implements the Chebyshev smoother")
+        if mode not in ('chebyshev', 'sa'):
+            raise NotImplementedError("the partitioned V-cycle implements the Chebyshev smoother (modes 'chebyshev', 'sa')")
         self.parts, self.comm, self.ops = parts, comm, ops or CudaOps()
         self.degree, self.ratio = int(degree), float(ratio)
         self._programs, self._tail_out = {}, None
@@ -687,7 +689,7 @@ class DistAMG:
         # ---- root: host hierarchy of the global matrix, shipped level by level
         payload, meta = None, None
         if comm.is_root():
-            host = AMGHierarchy(global_matrix() if callable(global_matrix) else global_matrix, mode='chebyshev',
+            host = AMGHierarchy(global_matrix() if callable(global_matrix) else global_matrix, mode=mode,
                                 max_levels=max_levels, reorder=False, upload=False)
             self.setup_host_seconds = host.setup_host_seconds
             sizes = host.level_sizes()
@@ -699,8 +701,7 @@ class DistAMG:
                     break
             offs = [list(offsets0)]
             for l in range(lsw):
-                csum = np.concatenate(([0], np.cumsum(host.splitting(l))))
-                offs.append([int(csum[o]) for o in offs[l]])
+                offs.append(host.coarse_offsets(l, offs[l]))
             payload = [torch.tensor([nl, lsw] + [o for lv in offs for o in lv], dtype=torch.int64, device=dev)]
 
             def put(M):
@@ -713,6 +714,8 @@ class DistAMG:
                 put(host.level_matrix(l, 1))
                 put(host.level_matrix(l, 2))
             put(host.level_matrix(lsw, 0))
+            if mode == 'sa':                   # the replicated tail continues the aggregation from level lsw
+                payload.append(torch.from_numpy(host.level_candidates(lsw)).to(dev))
             del host
         payload = comm.broadcast_tensors(payload)
         head = payload[0].cpu().numpy()
@@ -739,8 +742,14 @@ class DistAMG:
         A_sw = trip()
         n_sw = A_sw[0].numel() - 1
         tail = DeviceCSR(A_sw[0], A_sw[1], A_sw[2], (n_sw, n_sw))
-        self.tail = AMGHierarchy(tail, mode='chebyshev', degree=self.degree, max_levels=max(1, max_levels - lsw),
-                                 reorder=False)
+        if mode == 'sa':
+            cand_sw = next(it)
+            self.tail = AMGHierarchy(tail, mode='sa', degree=self.degree, max_levels=max(1, max_levels - lsw),
+                                     reorder=False, candidates=cand_sw, block_size=(cand_sw.shape[1] if lsw > 0 else 1),
+                                     first_level=lsw)
+        else:
+            self.tail = AMGHierarchy(tail, mode='chebyshev', degree=self.degree, max_levels=max(1, max_levels - lsw),
+                                     reorder=False)
         self.tail.set_chebyshev(self.degree, self.ratio)
         # ---- per level work vectors, inverse diagonals, spectral radius estimates
         ops = self.ops

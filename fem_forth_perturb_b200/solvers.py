@@ -82,7 +82,12 @@ class Reordering:
         torch = L.require_cuda()
         dev = A.d_data.device
         key = (A.pattern_key, A.nnz)
-        ent = self._patterns.get(key)
+        patterns = self.__dict__.setdefault('_patterns', {})
+        ent = patterns.get(key)
+        meta = {}
+        for attr in ('coords', 'candidates'):                       # per-DOF metadata follows the rows
+            src = getattr(A, attr, None)
+            meta[attr] = None if src is None else (lambda src=src: src()[self.perm.long()])
         if ent is not None:
             if ent['vmap'] is None:                                     # second use: pay for the map once
                 ids = torch.arange(A.nnz, dtype=torch.float64, device=dev)
@@ -99,7 +104,7 @@ class Reordering:
             else:
                 vals = out[2] if out is not None else torch.empty(A.nnz, dtype=torch.float64, device=dev)
             _gather_values(A.d_data, ent['vmap'], vals)
-            return DeviceCSR(ent['indptr'], ent['indices'], vals, A.shape)
+            return DeviceCSR(ent['indptr'], ent['indices'], vals, A.shape, **meta)
         if out is None:
             out = (torch.empty(self.n + 1, dtype=torch.int64, device=dev),
                    torch.empty(A.nnz, dtype=torch.int32, device=dev),
@@ -108,9 +113,9 @@ class Reordering:
                                         L.ptr(self.perm), L.ptr(self.iperm), L.ptr(out[0]), L.ptr(out[1]),
                                         L.ptr(out[2]), L.stream()), 'mwx_csr_permute')
         # keep the pattern tensors of the source alive with the entry: the key is made of their addresses
-        self._patterns[key] = dict(indptr=out[0].clone(), indices=out[1].clone(), vmap=None, scratch=None,
-                                   source=(A.d_indptr, A.d_indices))
-        return DeviceCSR(out[0], out[1], out[2], A.shape)
+        patterns[key] = dict(indptr=out[0].clone(), indices=out[1].clone(), vmap=None, scratch=None,
+                             source=(A.d_indptr, A.d_indices))
+        return DeviceCSR(out[0], out[1], out[2], A.shape, **meta)
 
     def _gather(self, v, idx):
         torch = L.require_cuda()
@@ -131,13 +136,20 @@ class AMGHierarchy:
     mode: 'parity' = symmetric lexicographic Gauss-Seidel (pyamg's default; iteration-count parity),
           'chebyshev' = Chebyshev(degree) smoothing (fast), 'jacobi' = 2 damped Jacobi steps (fast).
     """
-    MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2}
+    MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2, 'sa': 1}
 
-    def __init__(self, A, mode='parity', degree=2, theta=0.25, max_levels=10, max_coarse=10, reorder=None,
-                 upload=True):
+    def __init__(self, A, mode='parity', degree=2, theta=None, max_levels=10, max_coarse=None, reorder=None,
+                 upload=True, candidates=None, block_size=1, first_level=0):
+        """mode 'sa' (throughput, no reference counterpart): smoothed-aggregation hierarchy on the near-nullspace
+        candidates of A (``A.candidates`` - attached by ``asm_gpu`` on a Morley basis: the interpolants of 1, x, y -
+        or the ``candidates`` argument, (n, k)), Chebyshev smoothing.  The other modes use pyamg's Ruge-Stueben
+        hierarchy (theta 0.25, max_coarse 10)."""
         torch = L.require_cuda()
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {list(self.MODES)}")
+        sa = mode == 'sa'
+        theta = (0.1 if sa else 0.25) if theta is None else theta
+        max_coarse = (300 if sa else 10) if max_coarse is None else max_coarse
         lib = L.lib()
         A = _to_device_csr(A)
         self.n, self.mode = A.shape[0], mode
@@ -146,10 +158,20 @@ class AMGHierarchy:
             reorder = mode != 'parity'
         if reorder and mode == 'parity':
             raise ValueError("parity mode reproduces lexicographic Gauss-Seidel in skfem's numbering; reorder=False")
+        cand = None
+        if sa:
+            cand = candidates if candidates is not None else (A.candidates() if getattr(A, 'candidates', None) else None)
+            if cand is None:
+                raise ValueError("mode='sa' needs near-nullspace candidates: matrices assembled by asm_gpu on a Morley "
+                                 "basis carry them (also through condense); otherwise pass candidates=(n, k)")
+            if isinstance(cand, np.ndarray):
+                cand = torch.from_numpy(np.ascontiguousarray(cand, dtype=np.float64)).to(A.d_data.device)
         t0 = time.perf_counter()
         self.reordering = Reordering.for_matrix(A) if reorder else None
         if self.reordering is not None:
             A = self.reordering.matrix(A)
+            if cand is not None:
+                cand = cand[self.reordering.perm.long()]
             torch.cuda.synchronize()
         self.reorder_seconds = time.perf_counter() - t0
         t0 = time.perf_counter()
@@ -159,8 +181,16 @@ class AMGHierarchy:
         self._host = ctypes.c_void_p()
         import os
         lib.mwx_set_host_threads(int(os.environ.get('MWX_HOST_THREADS', os.cpu_count() or 1)))
-        L.check(lib.mwx_amg_setup_host(self.n, L.ptr(ip), L.ptr(ix), L.ptr(va), float(theta), int(max_levels),
-                                       int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_host')
+        if sa:
+            Bh = np.ascontiguousarray(cand.cpu().numpy() if hasattr(cand, 'cpu') else cand, dtype=np.float64)
+            if Bh.ndim != 2 or Bh.shape[0] != self.n or not 1 <= Bh.shape[1] <= 8:
+                raise ValueError("candidates must be an (n, k) array with 1 <= k <= 8")
+            L.check(lib.mwx_amg_setup_sa_host(self.n, L.ptr(ip), L.ptr(ix), L.ptr(va), L.ptr(Bh), Bh.shape[1],
+                                              int(block_size), int(first_level), float(theta), int(max_levels),
+                                              int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_sa_host')
+        else:
+            L.check(lib.mwx_amg_setup_host(self.n, L.ptr(ip), L.ptr(ix), L.ptr(va), float(theta), int(max_levels),
+                                           int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_host')
         self.levels = lib.mwx_amg_num_levels(self._host)
         self.setup_host_seconds = time.perf_counter() - t0
         self._dev = None
@@ -201,6 +231,27 @@ class AMGHierarchy:
         s = np.empty(rows, np.int32)
         L.check(L.lib().mwx_amg_level_splitting(self._host, level, L.ptr(s)), 'mwx_amg_level_splitting')
         return s
+
+    def level_candidates(self, level):
+        """(rows, k) near-nullspace candidates of a smoothed-aggregation level."""
+        k = ctypes.c_int32(0)
+        L.check(L.lib().mwx_amg_level_candidates(self._host, level, None, ctypes.byref(k)), 'mwx_amg_level_candidates')
+        B = np.empty((self.level_dims(level, 0)[0], k.value), dtype=np.float64)
+        L.check(L.lib().mwx_amg_level_candidates(self._host, level, L.ptr(B), ctypes.byref(k)), 'mwx_amg_level_candidates')
+        return B
+
+    def coarse_offsets(self, level, offsets):
+        """Row-block boundaries of level+1 induced by the boundaries ``offsets`` of ``level``: a coarse DOF goes with
+        the fine DOF it comes from (its C point, or the seed of its aggregate), so the blocks stay contiguous."""
+        k = ctypes.c_int32(0)
+        L.check(L.lib().mwx_amg_level_roots(self._host, level, None, ctypes.byref(k)), 'mwx_amg_level_roots')
+        if k.value == 0:                                   # Ruge-Stueben level
+            csum = np.concatenate(([0], np.cumsum(self.splitting(level))))
+            return [int(csum[o]) for o in offsets]
+        na = self.level_dims(level, 1)[1] // k.value
+        roots = np.empty(na, dtype=np.int64)
+        L.check(L.lib().mwx_amg_level_roots(self._host, level, L.ptr(roots), ctypes.byref(k)), 'mwx_amg_level_roots')
+        return [int(k.value * np.searchsorted(roots, o, side='left')) for o in offsets]
 
     def level_sizes(self):
         return [self.level_dims(l, 0)[0] for l in range(self.levels)]
@@ -489,7 +540,8 @@ class CondensePlan:
             if self._vmap is not None:
                 _gather_values(A.d_data, self._vmap, vals)
                 return DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out),
-                                 coords=self._coords_of(A, dev)), None
+                                 coords=self._rows_of(A, 'coords', dev),
+                                 candidates=self._rows_of(A, 'candidates', dev)), None
         bd = _to_device_vec(b, dev) if have_b else None
         xd = _to_device_vec(x, dev) if (have_b and x is not None) else None
         b_out = torch.empty(self.n_out, dtype=torch.float64, device=dev) if have_b else None
@@ -498,20 +550,21 @@ class CondensePlan:
                                           L.ptr(self.indices_out), L.ptr(vals), L.ptr(bd), L.ptr(xd), L.ptr(b_out),
                                           L.stream()), 'mwx_condense_fill')
         Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out),
-                         coords=self._coords_of(A, dev))
+                         coords=self._rows_of(A, 'coords', dev), candidates=self._rows_of(A, 'candidates', dev))
         return Aout, b_out
 
-    def _coords_of(self, A, dev):
-        if getattr(A, 'coords', None) is None:
+    def _rows_of(self, A, attr, dev):
+        """Per-DOF metadata of A (DOF locations, near-nullspace candidates) restricted to the kept rows."""
+        if getattr(A, attr, None) is None:
             return None
         torch = L.require_cuda()
-        src, plan = A.coords, self
+        src, plan = getattr(A, attr), self
 
-        def coords():
+        def rows():
             if plan._I_dev is None:
                 plan._I_dev = torch.from_numpy(np.ascontiguousarray(plan.I, dtype=np.int64)).to(dev)
             return src()[plan._I_dev]
-        return coords
+        return rows
 
 
 def condense(A, b=None, x=None, I=None, D=None, expand=True):

@@ -188,12 +188,28 @@ int mwx_amg_setup_host(int64_t n, const int64_t *indptr_host, const int32_t *ind
                        int32_t max_coarse, mwx_amg_host_t **out);
 int mwx_amg_num_levels(const mwx_amg_host_t *h);
 /* OpenMP threads of the host setup (launchers such as torchrun pin OMP_NUM_THREADS=1); returns the setting. */
+/* Throughput-mode hierarchy (no reference counterpart): smoothed aggregation with `ncand` near-nullspace candidates
+ * (row-major n x ncand; for the Morley stiffness the interpolants of 1, x, y).  Produces the same opaque hierarchy as
+ * mwx_amg_setup_host, so upload / V-cycle / PCG are shared; theta = symmetric strength threshold (0.1, halved per level). */
+int mwx_amg_setup_sa_host(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                          const double *candidates, int32_t ncand, int32_t block_size, int32_t first_level,
+                          double theta, int32_t max_levels, int32_t max_coarse, mwx_amg_host_t **out);
+/* block_size / first_level: 1 / 0 for a fine-level matrix.  To continue a hierarchy from one of its own coarse levels
+ * l (the partitioned solver replicates the small levels on every rank) pass that level's matrix, its candidates
+ * (mwx_amg_level_candidates), block_size = ncand and first_level = l: the remaining levels come out identical. */
+int mwx_amg_level_candidates(const mwx_amg_host_t *h, int32_t level, double *candidates, int32_t *ncand);
 int mwx_set_host_threads(int32_t n);
 /* which: 0 = A_l, 1 = P_l (n_l x n_{l+1}), 2 = R_l (n_{l+1} x n_l).  dims_host = {rows, cols, nnz}. */
 int mwx_amg_level_dims(const mwx_amg_host_t *h, int32_t level, int32_t which, int64_t *dims_host);
 int mwx_amg_level_copy(const mwx_amg_host_t *h, int32_t level, int32_t which, int64_t *indptr_host,
                        int32_t *indices_host, double *values_host);
+/* Borrowed pointers into the host hierarchy (valid until mwx_amg_destroy_host): no staging copy. */
+int mwx_amg_level_view(const mwx_amg_host_t *h, int32_t level, int32_t which, const int64_t **indptr,
+                       const int32_t **indices, const double **values);
 /* C/F splitting of level `level` (1 = C) for tests. */
+/* Smoothed-aggregation levels: coarse DOFs coarse_per_root*a .. +coarse_per_root-1 belong to aggregate a, whose seed
+ * DOF is roots[a] (ascending; P.cols / coarse_per_root entries).  coarse_per_root = 0 on a Ruge-Stueben level. */
+int mwx_amg_level_roots(const mwx_amg_host_t *h, int32_t level, int64_t *roots, int32_t *coarse_per_root);
 int mwx_amg_level_splitting(const mwx_amg_host_t *h, int32_t level, int32_t *split_host);
 void mwx_amg_destroy_host(mwx_amg_host_t *h);
 

@@ -190,6 +190,31 @@ def test_partitioned_pcg_independent_of_partition_count(cuda):
 
 
 @pytest.mark.gpu
+def test_distributed_smoothed_aggregation_matches_single_gpu(cuda):
+    """mode='sa' through the partitioned V-cycle: aggregates are numbered by seed, so coarse levels stay row-blocked."""
+    torch = cuda
+    F, D, prob, Kc = _setup(6, 3, eps2=0.25)
+    from fem_forth_perturb_b200.solvers import Reordering, _run_pcg
+    ro = Reordering.for_matrix(Kc)
+    ro.perm, ro.iperm = prob.partition.perm, prob.partition.iperm
+    Kp = ro.matrix(Kc)
+    assert Kp.candidates is not None
+    amg = D.DistAMG(prob.parts, prob.comm, Kp, mode='sa', switch_rows=600)
+    assert amg.lsw >= 1
+    rng = np.random.default_rng(4)
+    b_new = torch.from_numpy(rng.standard_normal(Kc.shape[0])).cuda()
+    single = F.AMGHierarchy(Kp, mode='sa', reorder=False)
+    z_ref = single.precondition(b_new)
+    z = torch.cat(amg.apply([b_new[p.lo:p.hi].clone() for p in prob.parts]))
+    assert float(torch.linalg.norm(z - z_ref) / torch.linalg.norm(z_ref)) < 1e-8
+    xs, its, info, _ = D.dist_pcg(prob.parts, prob.comm, [b_new[p.lo:p.hi].clone() for p in prob.parts], tol=1e-8,
+                                  precond='amg', amg=amg)
+    x1, its1, info1, _ = _run_pcg(Kp, b_new, 1e-8, None, amg=single, reordering=None)
+    assert info == 0 and info1 == 0 and abs(its - its1) <= 1
+    assert float(torch.linalg.norm(torch.cat(xs) - x1) / torch.linalg.norm(x1)) < 1e-6
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('nparts', [1, 2, 4])
 def test_distributed_vcycle_matches_single_gpu_fast_mode(cuda, nparts):
     """Global hierarchy applied as a collective V-cycle: same iteration count as the single-GPU fast mode."""

@@ -128,6 +128,117 @@ def test_native_amg_setup_matches_oracle_hierarchy(level, eps):
             assert abs(R - ml.P[l].T).max() <= 1e-14
 
 
+def _morley_system_with_candidates(level, eps):
+    """Condensed K2 of the oracle plus the Morley interpolants of 1, x, y restricted to the free DOFs."""
+    from oracle.skfem_mesh import MeshTri
+    from oracle.skfem_basis import InteriorBasis
+    from oracle import pipeline as pl
+    m = MeshTri().refine(level)
+    K = pl.assemble_K2(InteriorBasis(m, 'Morley', 5, shift=True), eps)
+    bf = m.boundary_facets()
+    D = np.concatenate((m.boundary_nodes(), bf + m.nv))
+    I = np.setdiff1d(np.arange(K.shape[0]), D)
+    A = K[I][:, I].tocsr()
+    A.sort_indices()
+    d = m.p[:, m.facets[1]] - m.p[:, m.facets[0]]
+    ln = np.sqrt((d ** 2).sum(0))
+    B = np.zeros((K.shape[0], 3))
+    B[:m.nv, 0], B[:m.nv, 1], B[:m.nv, 2] = 1.0, m.p[0], m.p[1]
+    B[m.nv:, 1], B[m.nv:, 2] = d[1] / ln, -d[0] / ln
+    # the fourth-order part annihilates the candidates (sign convention of the facet normals)
+    Kh = pl.assemble_K2(InteriorBasis(m, 'Morley', 5, shift=True), 1.0) - pl.assemble_K2(InteriorBasis(m, 'Morley', 5, shift=True), 0.0)
+    assert abs(Kh @ B).max() <= 1e-12 * abs(Kh).max()
+    return A, np.ascontiguousarray(B[I])
+
+
+def test_smoothed_aggregation_host_setup():
+    """mwx_amg_setup_sa_host: Galerkin consistency, seed-ordered aggregates, and a V-cycle that beats the
+    Ruge-Stueben hierarchy on the fourth-order-dominated problem (the reason the mode exists)."""
+    lib = L.lib()
+    A, B = _morley_system_with_candidates(5, 0.5)
+    n = A.shape[0]
+    ip, ix, va = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.astype(np.float64)
+    h = ctypes.c_void_p()
+    L.check(lib.mwx_amg_setup_sa_host(n, L.ptr(ip), L.ptr(ix), L.ptr(va), L.ptr(B), 3, 1, 0, 0.1, 10, 100, ctypes.byref(h)))
+    nl = lib.mwx_amg_num_levels(h)
+    assert nl >= 3
+
+    def mat(l, which):
+        dims = np.zeros(3, np.int64)
+        L.check(lib.mwx_amg_level_dims(h, l, which, L.ptr(dims)))
+        r, c, nnz = (int(v) for v in dims)
+        p = np.empty(r + 1, np.int64); j = np.empty(nnz, np.int32); v = np.empty(nnz)
+        L.check(lib.mwx_amg_level_copy(h, l, which, L.ptr(p), L.ptr(j), L.ptr(v)))
+        return sp.csr_matrix((v, j, p), shape=(r, c))
+    As = [mat(l, 0) for l in range(nl)]
+    Ps = [mat(l, 1) for l in range(nl - 1)]
+    assert abs(As[0] - A).max() == 0.0
+    for l in range(nl - 1):
+        assert As[l + 1].shape[0] % 3 == 0 and As[l + 1].shape[0] < As[l].shape[0] / 3
+        assert abs(mat(l, 2) - Ps[l].T).max() == 0.0
+        G = (Ps[l].T @ As[l] @ Ps[l]).tocsr()
+        dead = G.diagonal() == 0.0               # a candidate that vanishes on its aggregate: unit diagonal instead
+        assert dead.sum() < 0.2 * len(dead)
+        assert abs(G + sp.diags(dead.astype(float)) - As[l + 1]).max() <= 1e-12 * abs(G).max()
+        assert np.all(As[l + 1].diagonal() > 0)
+        # aggregates are numbered by their seed DOF: roots ascending, 3 coarse DOFs each
+        k = ctypes.c_int32(0)
+        roots = np.empty(Ps[l].shape[1] // 3, np.int64)
+        L.check(lib.mwx_amg_level_roots(h, l, L.ptr(roots), ctypes.byref(k)))
+        assert k.value == 3 and np.all(np.diff(roots) > 0) and roots[-1] < As[l].shape[0]
+        with pytest.raises(L.MwxError):
+            L.check(lib.mwx_amg_level_splitting(h, l, L.ptr(np.empty(As[l].shape[0], np.int32))))
+    # continuing from a coarse level of the same hierarchy reproduces the remaining levels (replicated tail)
+    k = ctypes.c_int32(0)
+    B1 = np.empty((As[1].shape[0], 3))
+    L.check(lib.mwx_amg_level_candidates(h, 1, L.ptr(B1), ctypes.byref(k)))
+    assert k.value == 3
+    A1 = As[1]
+    ip1, ix1, va1 = A1.indptr.astype(np.int64), A1.indices.astype(np.int32), A1.data.astype(np.float64)
+    h1 = ctypes.c_void_p()
+    L.check(lib.mwx_amg_setup_sa_host(A1.shape[0], L.ptr(ip1), L.ptr(ix1), L.ptr(va1), L.ptr(B1), 3, 3, 1, 0.1, 9, 100,
+                                      ctypes.byref(h1)))
+    assert lib.mwx_amg_num_levels(h1) == nl - 1
+    for l in range(1, nl):
+        dims = np.zeros(3, np.int64)
+        L.check(lib.mwx_amg_level_dims(h1, l - 1, 0, L.ptr(dims)))
+        assert (int(dims[0]), int(dims[2])) == (As[l].shape[0], As[l].nnz)
+        v = np.empty(int(dims[2])); pp = np.empty(int(dims[0]) + 1, np.int64); jj = np.empty(int(dims[2]), np.int32)
+        L.check(lib.mwx_amg_level_copy(h1, l - 1, 0, L.ptr(pp), L.ptr(jj), L.ptr(v)))
+        assert np.array_equal(v, As[l].data) and np.array_equal(jj, As[l].indices)
+    lib.mwx_amg_destroy_host(h1)
+    lib.mwx_amg_destroy_host(h)
+
+    def vcycle_pcg(As, Ps):
+        dinv = [1.0 / a.diagonal() for a in As]
+        coarse = np.linalg.pinv(As[-1].toarray())
+
+        def cyc(l, b):
+            if l == len(As) - 1:
+                return coarse @ b
+            x = 0.6 * dinv[l] * b
+            x = x + 0.6 * dinv[l] * (b - As[l] @ x)
+            x = x + Ps[l] @ cyc(l + 1, Ps[l].T @ (b - As[l] @ x))
+            x = x + 0.6 * dinv[l] * (b - As[l] @ x)
+            return x + 0.6 * dinv[l] * (b - As[l] @ x)
+        rng = np.random.default_rng(0)
+        b = A @ rng.uniform(-1, 1, n)
+        x = np.zeros(n); r = b.copy(); z = cyc(0, r); p = z.copy(); rz = r @ z
+        for it in range(1, 500):
+            q = A @ p; a = rz / (p @ q); x += a * p; r -= a * q
+            if np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b):
+                return it
+            z = cyc(0, r); rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
+        return 500
+    from oracle.pyamg_rs import RugeStuben
+    rs = RugeStuben(A)
+    its_sa, its_rs = vcycle_pcg(As, Ps), vcycle_pcg(list(rs.A), list(rs.P))
+    assert its_sa < 0.6 * its_rs, (its_sa, its_rs)
+    # bad arguments
+    assert lib.mwx_amg_setup_sa_host(n, L.ptr(ip), L.ptr(ix), L.ptr(va), None, 3, 1, 0, 0.1, 10, 100, ctypes.byref(h)) == -1
+    assert lib.mwx_amg_setup_sa_host(n, L.ptr(ip), L.ptr(ix), L.ptr(va), L.ptr(B), 9, 1, 0, 0.1, 10, 100, ctypes.byref(h)) == -1
+
+
 def test_amg_setup_tiny_and_bad_arguments():
     lib = L.lib()
     K = sp.identity(5, format='csr')
