@@ -212,8 +212,10 @@ void direct_interpolation(const Csr &A, const std::vector<uint8_t> &strong,
     }
 }
 
-// R = P^T.  Every thread owns a contiguous range of P's columns (= rows of R) and streams over all of P twice (count,
-// fill): sequential reads, no atomics, rows ascending inside every column - deterministic for any thread count.
+// R = P^T.  Every thread owns a contiguous range of P's columns (= rows of R) and streams twice (count, fill) over the
+// row blocks of P whose column span meets its range - sequential reads, no atomics, rows ascending inside every
+// column: deterministic for any thread count.  (Prolongators are banded in the solver's numbering: coarse DOFs are
+// numbered after the fine DOFs they come from, so a thread skips most blocks.)
 void transpose_csr(const Csr &P, Csr &R) {
     R.rows = P.cols; R.cols = P.rows;
     R.ptr.assign((size_t)R.rows + 1, 0);
@@ -223,7 +225,19 @@ void transpose_csr(const Csr &P, Csr &R) {
     nthreads = omp_get_max_threads();
 #endif
     if ((int64_t)P.idx.size() < (int64_t)1 << 16) nthreads = 1;
-    const int64_t nnz = (int64_t)P.idx.size();
+    constexpr int64_t BLK = 4096;
+    const int64_t nblk = (P.rows + BLK - 1) / BLK;
+    std::vector<int32_t> bmin((size_t)nblk, std::numeric_limits<int32_t>::max()), bmax((size_t)nblk, -1);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t b = 0; b < nblk; ++b) {
+        const int64_t r1 = std::min(P.rows, (b + 1) * BLK);
+        int32_t lo = std::numeric_limits<int32_t>::max(), hi = -1;
+        for (int64_t k = P.ptr[(size_t)(b * BLK)]; k < P.ptr[(size_t)r1]; ++k) {
+            lo = std::min(lo, P.idx[(size_t)k]);
+            hi = std::max(hi, P.idx[(size_t)k]);
+        }
+        bmin[(size_t)b] = lo; bmax[(size_t)b] = hi;
+    }
 #pragma omp parallel num_threads(nthreads)
     {
         int t = 0;
@@ -231,9 +245,13 @@ void transpose_csr(const Csr &P, Csr &R) {
         t = omp_get_thread_num();
 #endif
         const int32_t c0 = (int32_t)(R.rows * t / nthreads), c1 = (int32_t)(R.rows * (t + 1) / nthreads);
-        for (int64_t k = 0; k < nnz; ++k) {
-            const int32_t j = P.idx[(size_t)k];
-            if (j >= c0 && j < c1) ++R.ptr[(size_t)j + 1];
+        for (int64_t b = 0; b < nblk; ++b) {
+            if (bmax[(size_t)b] < c0 || bmin[(size_t)b] >= c1) continue;
+            const int64_t r1 = std::min(P.rows, (b + 1) * BLK);
+            for (int64_t k = P.ptr[(size_t)(b * BLK)]; k < P.ptr[(size_t)r1]; ++k) {
+                const int32_t j = P.idx[(size_t)k];
+                if (j >= c0 && j < c1) ++R.ptr[(size_t)j + 1];
+            }
         }
     }
     for (int64_t i = 0; i < R.rows; ++i) R.ptr[(size_t)i + 1] += R.ptr[(size_t)i];
@@ -245,14 +263,18 @@ void transpose_csr(const Csr &P, Csr &R) {
         t = omp_get_thread_num();
 #endif
         const int32_t c0 = (int32_t)(R.rows * t / nthreads), c1 = (int32_t)(R.rows * (t + 1) / nthreads);
-        for (int64_t i = 0; i < P.rows; ++i)
-            for (int64_t k = P.ptr[(size_t)i]; k < P.ptr[(size_t)i + 1]; ++k) {
-                const int32_t j = P.idx[(size_t)k];
-                if (j >= c0 && j < c1) {
-                    const int64_t o = cur[(size_t)j]++;
-                    R.idx[(size_t)o] = (int32_t)i; R.val[(size_t)o] = P.val[(size_t)k];
+        for (int64_t b = 0; b < nblk; ++b) {
+            if (bmax[(size_t)b] < c0 || bmin[(size_t)b] >= c1) continue;
+            const int64_t r1 = std::min(P.rows, (b + 1) * BLK);
+            for (int64_t i = b * BLK; i < r1; ++i)
+                for (int64_t k = P.ptr[(size_t)i]; k < P.ptr[(size_t)i + 1]; ++k) {
+                    const int32_t j = P.idx[(size_t)k];
+                    if (j >= c0 && j < c1) {
+                        const int64_t o = cur[(size_t)j]++;
+                        R.idx[(size_t)o] = (int32_t)i; R.val[(size_t)o] = P.val[(size_t)k];
+                    }
                 }
-            }
+        }
     }
 }
 
@@ -608,17 +630,26 @@ double sa_rho_dinv_a(const Csr &A, const std::vector<double> &dinv, int iters) {
         v[(size_t)i] = (double)(z >> 11) / 9007199254740992.0 - 0.5;
     }
     double lam = 1.0;
+    constexpr int64_t CH = 8192;                             // fixed chunks: the sums do not depend on the thread count
+    const int64_t nch = (n + CH - 1) / CH;
+    std::vector<double> pv((size_t)nch), pw((size_t)nch);
     for (int it = 0; it < iters; ++it) {
-        double nv = 0.0, nw = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : nv, nw)
-        for (int64_t i = 0; i < n; ++i) {
-            double sum = 0.0;
-            for (int64_t k = A.ptr[(size_t)i]; k < A.ptr[(size_t)i + 1]; ++k) sum += A.val[(size_t)k] * v[(size_t)A.idx[(size_t)k]];
-            sum *= dinv[(size_t)i];
-            w[(size_t)i] = sum;
-            nw += sum * sum;
-            nv += v[(size_t)i] * v[(size_t)i];
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nch; ++c) {
+            double nv = 0.0, nw = 0.0;
+            const int64_t i1 = std::min(n, (c + 1) * CH);
+            for (int64_t i = c * CH; i < i1; ++i) {
+                double sum = 0.0;
+                for (int64_t k = A.ptr[(size_t)i]; k < A.ptr[(size_t)i + 1]; ++k) sum += A.val[(size_t)k] * v[(size_t)A.idx[(size_t)k]];
+                sum *= dinv[(size_t)i];
+                w[(size_t)i] = sum;
+                nw += sum * sum;
+                nv += v[(size_t)i] * v[(size_t)i];
+            }
+            pv[(size_t)c] = nv; pw[(size_t)c] = nw;
         }
+        double nv = 0.0, nw = 0.0;
+        for (int64_t c = 0; c < nch; ++c) { nv += pv[(size_t)c]; nw += pw[(size_t)c]; }
         lam = std::sqrt(nw / nv);
         const double sc = 1.0 / std::sqrt(nw);
 #pragma omp parallel for schedule(static)
@@ -653,6 +684,8 @@ void sa_smooth_prolongator(const Csr &A, const Csr &T, const std::vector<double>
         std::vector<double> blk;
         auto &oi = bidx[(size_t)t];
         auto &ov = bval[(size_t)t];
+        oi.reserve((size_t)(first[(size_t)t + 1] - first[(size_t)t]) * nc * 4);      // ~4 aggregates per row
+        ov.reserve((size_t)(first[(size_t)t + 1] - first[(size_t)t]) * nc * 4);
         for (int64_t i = first[(size_t)t]; i < first[(size_t)t + 1]; ++i) {
             ids.clear(); blk.clear();
             auto add = [&](int64_t j, double a) {
