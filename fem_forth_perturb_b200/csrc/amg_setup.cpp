@@ -787,8 +787,12 @@ extern "C" int mwx_amg_setup_sa_host(int64_t n, const int64_t *indptr, const int
             sa_strength(L.A, bs, theta * std::pow(0.5, (double)(first_level + (int)h->levels.size() - 1)), S);
             const auto t1 = now();
             std::vector<int32_t> agg;
-            const int64_t na = sa_aggregate(S, agg);
-            if (2 * na * ncand > nl) break;                // coarsening has stalled: this level is the coarsest
+            int64_t na = sa_aggregate(S, agg);
+            if (2 * na * ncand > nl) {                     // too few strong connections at this threshold:
+                sa_strength(L.A, bs, 0.0, S);              // aggregate over the whole pattern instead
+                na = sa_aggregate(S, agg);
+                if (2 * na * ncand > nl) break;            // coarsening has stalled: this level is the coarsest
+            }
             std::vector<int64_t> seeds;
             sa_order_by_seed(agg, na, seeds);
             L.roots.resize((size_t)na);

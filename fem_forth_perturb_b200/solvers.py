@@ -199,6 +199,10 @@ class AMGHierarchy:
             return
         t1 = time.perf_counter()
         # coarsest level: dense pseudo-inverse (scipy 1.4.1 pinv2 semantics) through LAPACK
+        if self.level_dims(self.levels - 1, 0)[0] > 8192:
+            raise RuntimeError(f"AMG coarsening stopped at {self.level_dims(self.levels - 1, 0)[0]} rows (levels "
+                               f"{self.level_sizes()}): too large for the dense coarse solve; raise max_levels or "
+                               f"lower theta")
         Ac = self.level_matrix(self.levels - 1, 0).toarray()
         u, s, vh = np.linalg.svd(Ac, full_matrices=False)
         rank = int(np.sum(s > 1e6 * np.finfo(np.float64).eps * s.max())) if s.size else 0
