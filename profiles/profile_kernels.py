@@ -1,5 +1,5 @@
 """Short driver for ncu: level-L K2 assembly, condense, SpMV and a few PCG iterations.
-    python profiles/profile_kernels.py [level] [pcg_maxiter]
+    python profiles/profile_kernels.py [level] [pcg_maxiter] [amg mode: sa | chebyshev]
 """
 import os
 import sys
@@ -14,6 +14,7 @@ from fem_forth_perturb_b200.solvers import _run_pcg
 
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 maxit = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+amg_mode = sys.argv[3] if len(sys.argv) > 3 else 'sa'
 gm = F.MeshTri().refine(level)
 basis = F.InteriorBasis(gm, F.ElementTriMorley())
 form = 1e-4 * F.a_load + F.b_load
@@ -34,10 +35,10 @@ for _ in range(3):
 torch.cuda.synchronize()
 if maxit:
     b = Kc.dot(x)
-    ml = F.AMGHierarchy(Kc, mode='chebyshev')
+    ml = F.AMGHierarchy(Kc, mode=amg_mode, reorder=False)
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        _run_pcg(Kc, b, 1e-8, maxit, amg=ml)
+        _run_pcg(Kc, b, 1e-8, maxit, amg=ml, reordering=None)
 torch.cuda.synchronize()
 print('done', n, Kc.nnz)
