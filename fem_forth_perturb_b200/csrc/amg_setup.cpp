@@ -32,11 +32,32 @@
 
 namespace {
 
+// std::vector whose resize() leaves new elements uninitialised: the big index/value arrays are always filled right
+// after they are sized, in parallel - a serial zero-fill (and its first touch of every page from one thread) would
+// cost seconds at 10^9 entries.
+template <typename T>
+struct DefaultInit : std::allocator<T> {
+    template <typename U> struct rebind { using other = DefaultInit<U>; };
+    using std::allocator<T>::allocator;
+    template <typename U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+    template <typename U, typename... Args> void construct(U *p, Args &&...args) {
+        ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
+    }
+};
+template <typename T> using Vec = std::vector<T, DefaultInit<T>>;
+
+template <typename T>
+void parallel_copy(const T *src, size_t n, Vec<T> &dst) {
+    dst.resize(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) dst[(size_t)i] = src[(size_t)i];
+}
+
 struct Csr {
     int64_t rows = 0, cols = 0;
-    std::vector<int64_t> ptr;
-    std::vector<int32_t> idx;
-    std::vector<double> val;
+    Vec<int64_t> ptr;
+    Vec<int32_t> idx;
+    Vec<double> val;
     int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
 };
 
@@ -374,9 +395,9 @@ extern "C" int mwx_amg_setup_host(int64_t n, const int64_t *indptr, const int32_
         h->levels.emplace_back();
         Csr &A0 = h->levels.back().A;
         A0.rows = A0.cols = n;
-        A0.ptr.assign(indptr, indptr + n + 1);
-        A0.idx.assign(indices, indices + indptr[n]);
-        A0.val.assign(values, values + indptr[n]);
+        parallel_copy(indptr, (size_t)n + 1, A0.ptr);
+        parallel_copy(indices, (size_t)indptr[n], A0.idx);
+        parallel_copy(values, (size_t)indptr[n], A0.val);
         const bool prof = std::getenv("MWX_AMG_PROFILE") != nullptr;
         auto now = [] { return std::chrono::steady_clock::now(); };
         auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -661,6 +682,7 @@ double sa_rho_dinv_a(const Csr &A, const std::vector<double> &dinv, int iters) {
 // P = (I - omega D^-1 A) T, columns sorted.  Every thread takes one contiguous block of rows and appends to its own
 // buffers (one pass, no per-row allocations); the blocks are then laid end to end.
 void sa_smooth_prolongator(const Csr &A, const Csr &T, const std::vector<double> &dinv, double omega, Csr &P) {
+    const auto tt0 = std::chrono::steady_clock::now();
     const int64_t n = A.rows;
     P.rows = n; P.cols = T.cols;
     P.ptr.assign((size_t)n + 1, 0);
@@ -682,8 +704,8 @@ void sa_smooth_prolongator(const Csr &A, const Csr &T, const std::vector<double>
         const int nc = (int)(T.ptr[1] - T.ptr[0]);
         std::vector<int32_t> ids, ord;
         std::vector<double> blk;
-        auto &oi = bidx[(size_t)t];
-        auto &ov = bval[(size_t)t];
+        std::vector<int32_t> oi;             // thread-local (the shared vector headers would false-share on every push)
+        std::vector<double> ov;
         oi.reserve((size_t)(first[(size_t)t + 1] - first[(size_t)t]) * nc * 4);      // ~4 aggregates per row
         ov.reserve((size_t)(first[(size_t)t + 1] - first[(size_t)t]) * nc * 4);
         for (int64_t i = first[(size_t)t]; i < first[(size_t)t + 1]; ++i) {
@@ -705,7 +727,10 @@ void sa_smooth_prolongator(const Csr &A, const Csr &T, const std::vector<double>
                 for (int c = 0; c < nc; ++c) { oi.push_back(ids[(size_t)k] * nc + c); ov.push_back(blk[(size_t)k * nc + c]); }
             P.ptr[(size_t)i + 1] = (int64_t)ids.size() * nc;
         }
+        bidx[(size_t)t].swap(oi);
+        bval[(size_t)t].swap(ov);
     }
+    const auto tt1 = std::chrono::steady_clock::now();
     for (int64_t i = 0; i < n; ++i) P.ptr[(size_t)i + 1] += P.ptr[(size_t)i];
     P.idx.resize((size_t)P.ptr[(size_t)n]); P.val.resize((size_t)P.ptr[(size_t)n]);
 #pragma omp parallel for schedule(static, 1) num_threads(nthreads)
@@ -714,6 +739,10 @@ void sa_smooth_prolongator(const Csr &A, const Csr &T, const std::vector<double>
         std::copy(bidx[(size_t)t].begin(), bidx[(size_t)t].end(), P.idx.begin() + o);
         std::copy(bval[(size_t)t].begin(), bval[(size_t)t].end(), P.val.begin() + o);
     }
+    const auto tt2 = std::chrono::steady_clock::now();
+    if (std::getenv("MWX_AMG_PROFILE"))
+        std::fprintf(stderr, "[mwx sa]     smooth: rows %.3f assemble %.3f (threads %d)\n", std::chrono::duration<double>(tt1 - tt0).count(),
+                     std::chrono::duration<double>(tt2 - tt1).count(), nthreads);
 }
 
 // Dead coarse DOFs (a candidate that vanished on its aggregate) leave empty rows/columns: give them a unit
@@ -768,9 +797,9 @@ extern "C" int mwx_amg_setup_sa_host(int64_t n, const int64_t *indptr, const int
         h->levels.emplace_back();
         Csr &A0 = h->levels.back().A;
         A0.rows = A0.cols = n;
-        A0.ptr.assign(indptr, indptr + n + 1);
-        A0.idx.assign(indices, indices + indptr[n]);
-        A0.val.assign(values, values + indptr[n]);
+        parallel_copy(indptr, (size_t)n + 1, A0.ptr);
+        parallel_copy(indices, (size_t)indptr[n], A0.idx);
+        parallel_copy(values, (size_t)indptr[n], A0.val);
         std::vector<double> B(candidates, candidates + (size_t)n * ncand);
         int bs = block_size;                                 // > 1: the input is itself a coarse level of this scheme
         const bool prof = std::getenv("MWX_AMG_PROFILE") != nullptr;
