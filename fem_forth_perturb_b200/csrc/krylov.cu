@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                                                     const double *__restrict__ dot_with,
                                                     double *__restrict__ dot_out, double *partials,
                                                     unsigned int *ticket, SmootherArgs sm, int tma_ok,
-                                                    int rows_per_tile) {
+                                                    int rows_per_tile, int lanes_per_row) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     auto stage_vals = [&](int stage) { return reinterpret_cast<double *>(smem_raw + stage * SPMV_STAGE_BYTES); };
     auto stage_cols = [&](int stage) {
@@ -164,15 +164,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
             }
             __syncthreads();
         }
-        // one thread per row (a thread owns several rows when the tile is longer than the CTA)
-        for (int64_t r = r0 + tid; r < r1; r += SPMV_THREADS) {
-            const int64_t a = indptr[r], b = indptr[r + 1];
-            double sum = 0.0;
-            if (nst >= 0) {
-                for (int e = (int)(a - base); e < (int)(b - base); ++e) sum += vs[e];
-            } else {
-                for (int64_t e = a; e < b; ++e) sum += values[e] * __ldg(x + indices[e]);
-            }
+        auto finish = [&](int64_t r, double sum) {
             if (MODE == 1) sum = cvec[r] - sum;
             if (MODE == 2) sum = cvec[r] + sum;
             if (MODE == 3) {
@@ -182,6 +174,38 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
             }
             y[r] = sum;
             if (DOT) dacc += dot_with[r] * sum;
+        };
+        if (lanes_per_row == 1) {
+            // one thread per row (a thread owns several rows when the tile is longer than the CTA)
+            for (int64_t r = r0 + tid; r < r1; r += SPMV_THREADS) {
+                const int64_t a = indptr[r], b = indptr[r + 1];
+                double sum = 0.0;
+                if (nst >= 0) {
+                    for (int e = (int)(a - base); e < (int)(b - base); ++e) sum += vs[e];
+                } else {
+                    for (int64_t e = a; e < b; ++e) sum += values[e] * __ldg(x + indices[e]);
+                }
+                finish(r, sum);
+            }
+        } else {
+            // dense operators (AMG coarse levels, restriction: 50-80 nonzeros per row, 16-64 rows per tile): a group of
+            // 2-16 lanes shares a row, strided partial sums folded by shuffles in a fixed order
+            const int lpr = lanes_per_row, sub = tid & (lpr - 1), grp = tid / lpr, ngrp = SPMV_THREADS / lpr;
+            for (int64_t rb = r0; rb < r1; rb += ngrp) {           // CTA-uniform trip count: full-mask shuffles are safe
+                const int64_t r = rb + grp;
+                const bool valid = r < r1;
+                double sum = 0.0;
+                if (valid) {
+                    const int64_t a = indptr[r], b = indptr[r + 1];
+                    if (nst >= 0) {
+                        for (int e = (int)(a - base) + sub; e < (int)(b - base); e += lpr) sum += vs[e];
+                    } else {
+                        for (int64_t e = a + sub; e < b; e += lpr) sum += values[e] * __ldg(x + indices[e]);
+                    }
+                }
+                for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (valid && sub == 0) finish(r, sum);
+            }
         }
         __syncthreads();                 // stage fully consumed before thread 0 refills it next iteration
     }
@@ -363,7 +387,9 @@ int spmv_plan_rows(int64_t n, const int64_t *indptr, int *rows_out, cudaStream_t
     int rows = 8;
     for (int c = 0; c < SPMV_NCAND; ++c)
         if (h[c] <= SPMV_STAGE_ELEMS) { rows = cand[c]; break; }
-    *rows_out = rows;
+    // short tiles mean long rows: let 4 / 8 / 16 lanes share a row (encoded above the tile height, see spmv_launch)
+    const int lpr_log2 = rows <= 16 ? 4 : (rows <= 32 ? 3 : (rows <= 64 ? 2 : 0));
+    *rows_out = rows + 4096 * lpr_log2;
     return 0;
 }
 
@@ -383,9 +409,11 @@ int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *in
     }
     // TMA bulk copies need 16-byte aligned global addresses; the kernel aligns offsets, the bases must be too
     const int tma_ok = (((uintptr_t)values & 15) == 0 && ((uintptr_t)indices & 15) == 0) ? 1 : 0;
-    const int rows = nnz <= -8 ? (int)(-nnz) : spmv_rows_per_tile(n, nnz);    // nnz <= -8: planned tile height
+    // nnz <= -8: a plan from spmv_plan_rows = -(tile height + 4096 * log2(lanes per row))
+    const int plan = nnz <= -8 ? (int)(-nnz) : spmv_rows_per_tile(n, nnz);
+    const int rows = plan & 4095, lanes = 1 << (plan >> 12);
     k_spmv<DOT, MODE><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SPMV_SMEM_BYTES, st>>>(
-        n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows);
+        n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows, lanes);
     MWX_LAUNCH_CHECK();
     return 0;
 }

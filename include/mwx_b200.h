@@ -163,7 +163,8 @@ int mwx_smoother_first(int64_t n, const double *b, const double *dinv, double c2
                        void *stream);
 /* out = M v for a dense row-major n x n M (coarsest-level pseudo-inverse). */
 int mwx_dense_gemv(int64_t n, const double *M, const double *v, double *out, void *stream);
-/* Tallest SpMV row tile whose every tile fits one TMA stage; pass -(tile_rows) as `nnz` to mwx_spmv. */
+/* SpMV plan of an operator: the tallest row tile whose every tile fits one TMA stage, plus (for dense operators with
+ * 16-64 rows per tile) how many lanes share a row, packed as rows + 4096*log2(lanes).  Opaque: pass -(plan) as `nnz`. */
 int mwx_spmv_plan(int64_t n, const int64_t *indptr, int32_t *tile_rows_host, void *stream);
 /* diag[i] = A[i,i] (0 if absent): build_pc_diag, ref main/example1/utils.py:48-50. */
 int mwx_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices,
