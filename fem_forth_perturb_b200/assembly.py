@@ -236,7 +236,8 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
         L.check(lib.mwx_assemble_lagrange_laplace(ubasis.N, m.nt, ubasis.Nbfun, L.ptr(m.d_pxy), L.ptr(m.d_t),
                                                   L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']),
                                                   L.ptr(pat['indptr']), L.ptr(vals), st), 'mwx_assemble_lagrange_laplace')
-        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords)
+        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords,
+                      candidates=ubasis.constant_candidates)
         scale = f.terms['laplace']
         K = K if scale == 1.0 else scale * K
         return K.eliminate_zeros()              # skfem: COO.eliminate_zeros() -> 5-point pattern on this mesh

@@ -132,6 +132,12 @@ class InteriorBasis:
                 self._coords = pxy.contiguous()
         return self._coords
 
+    def constant_candidates(self):
+        """Device (N, 1) of ones: the near-nullspace of a second-order operator (`laplace` on P1 / P2 - every DOF of
+        those elements is a point value)."""
+        torch = L.require_cuda()
+        return torch.ones(self.N, 1, dtype=torch.float64, device=self.mesh.device)
+
     def nullspace_candidates(self):
         """Device (N, 3) fp64: the interpolants of 1, x, y in this basis - the near-nullspace of the stiffness
         eps^2 (hess:hess) + (grad.grad) that smoothed aggregation is built on.  Morley: vertex DOFs (1, x, y),

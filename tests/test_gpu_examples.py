@@ -86,6 +86,19 @@ def test_example1_tables_match_reference_logs(cuda, golden_norms, golden_iterati
     assert any('epsilon = 1' in ' '.join(map(str, l)) for l in lines)
 
 
+def test_example1_in_sa_mode_reproduces_the_table(cuda, golden_norms):
+    """The throughput mode (smoothed aggregation; constant candidate for the w-problem, Morley interpolants of 1, x, y
+    for the u-problem) solves the same systems: the printed table still matches the reference's log to 3 digits."""
+    sys.path.insert(0, os.path.join(ROOT, 'examples'))
+    import example1
+    results, its = example1.run(refine_time=6, epsilon_range=2, element_type='P1', mode='sa', out=lambda *a: None)
+    g = golden_norms['ex1_P1_nopen']
+    for eps, tab in results.items():
+        gold = np.array(g['rows'][repr(float(eps))])
+        assert (np.abs(tab - gold) / np.abs(gold)).max() < 5e-4, eps
+    assert max(p[1] for pairs in its.values() for p in pairs) < 40
+
+
 def test_penalty_example_tables_match_reference_logs(cuda, golden_norms):
     """solve_problem2 (Nitsche penalty, nodal-only BCs, L2pnvError) on the device vs log/ex3_range_2/ex3_P1_pen."""
     sys.path.insert(0, os.path.join(ROOT, 'examples'))
