@@ -345,7 +345,7 @@ def _make_krylov(print_iters, krylov=None, verbose=False, **kwargs):
     def run(A, b, **solve_time_kwargs):
         kwargs.update(solve_time_kwargs)
         kw = dict(kwargs)
-        pre = bool(kw.pop('Precondition', False)) is True
+        pre = kw.pop('Precondition', False) == True   # noqa: E712 - the reference's own test (utils.py:283)
         reorder = bool(kw.pop('reorder', False))
         _reject_host_callables(kw)
         t0 = time.perf_counter()
