@@ -239,6 +239,40 @@ def test_smoothed_aggregation_host_setup():
     assert lib.mwx_amg_setup_sa_host(n, L.ptr(ip), L.ptr(ix), L.ptr(va), L.ptr(B), 9, 1, 0, 0.1, 10, 100, ctypes.byref(h)) == -1
 
 
+def test_host_setups_do_not_depend_on_the_thread_count():
+    """Both hierarchies come out bit-identical with 1 and with many host threads (the partitioned solver rebuilds the
+    coarse tail on every rank and relies on it)."""
+    lib = L.lib()
+    A, B = _morley_system_with_candidates(5, 0.3)
+    n = A.shape[0]
+    ip, ix, va = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.astype(np.float64)
+
+    def levels(sa, threads):
+        lib.mwx_set_host_threads(threads)
+        h = ctypes.c_void_p()
+        if sa:
+            L.check(lib.mwx_amg_setup_sa_host(n, L.ptr(ip), L.ptr(ix), L.ptr(va), L.ptr(B), 3, 1, 0, 0.1, 10, 50, ctypes.byref(h)))
+        else:
+            L.check(lib.mwx_amg_setup_host(n, L.ptr(ip), L.ptr(ix), L.ptr(va), 0.25, 10, 10, ctypes.byref(h)))
+        out = []
+        for l in range(lib.mwx_amg_num_levels(h)):
+            for which in (0, 1):
+                dims = np.zeros(3, np.int64)
+                if lib.mwx_amg_level_dims(h, l, which, L.ptr(dims)) != 0:
+                    continue
+                p = np.empty(int(dims[0]) + 1, np.int64); j = np.empty(int(dims[2]), np.int32); v = np.empty(int(dims[2]))
+                L.check(lib.mwx_amg_level_copy(h, l, which, L.ptr(p), L.ptr(j), L.ptr(v)))
+                out.append((p, j, v))
+        lib.mwx_amg_destroy_host(h)
+        return out
+    for sa in (False, True):
+        one, many = levels(sa, 1), levels(sa, 7)
+        assert len(one) == len(many) and len(one) >= 4
+        for (p1, j1, v1), (p2, j2, v2) in zip(one, many):
+            assert np.array_equal(p1, p2) and np.array_equal(j1, j2) and np.array_equal(v1, v2)
+    lib.mwx_set_host_threads(os.cpu_count() or 1)
+
+
 def test_amg_setup_tiny_and_bad_arguments():
     lib = L.lib()
     K = sp.identity(5, format='csr')
