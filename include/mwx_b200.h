@@ -191,7 +191,7 @@ int mwx_amg_num_levels(const mwx_amg_host_t *h);
 /* OpenMP threads of the host setup (launchers such as torchrun pin OMP_NUM_THREADS=1); returns the setting. */
 /* Throughput-mode hierarchy (no reference counterpart): smoothed aggregation with `ncand` near-nullspace candidates
  * (row-major n x ncand; for the Morley stiffness the interpolants of 1, x, y).  Produces the same opaque hierarchy as
- * mwx_amg_setup_host, so upload / V-cycle / PCG are shared; theta = symmetric strength threshold (0.1, halved per level). */
+ * mwx_amg_setup_host, so upload / V-cycle / PCG are shared; theta = symmetric strength threshold (0.1, the same on every level). */
 int mwx_amg_setup_sa_host(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
                           const double *candidates, int32_t ncand, int32_t block_size, int32_t first_level,
                           double theta, int32_t max_levels, int32_t max_coarse, mwx_amg_host_t **out);
