@@ -6,12 +6,21 @@ in HBM so that ``eps**2 * A + B``, ``condense`` and the solvers stay on the devi
 canonical ``scipy.sparse.csr_matrix`` (skfem's DOF numbering, sorted indices) on demand.
 """
 import ctypes
+import itertools
 
 import numpy as np
 
 from . import _lib as L
 from .basis import FacetBasis, InteriorBasis
 from .forms import as_form
+
+_PATTERN_IDS = itertools.count(1)
+
+
+def new_pattern_id():
+    """Identity of a sparsity pattern: handed out once where a pattern is built and carried by every matrix that
+    shares it.  (Device addresses are not identities: the caching allocator hands freed addresses out again.)"""
+    return next(_PATTERN_IDS)
 
 
 class DeviceCSR:
@@ -20,7 +29,7 @@ class DeviceCSR:
     def __init__(self, indptr, indices, data, shape, pattern_key=None, coords=None, candidates=None):
         self.d_indptr, self.d_indices, self.d_data = indptr, indices, data
         self.shape = tuple(int(s) for s in shape)
-        self.pattern_key = pattern_key if pattern_key is not None else (indptr.data_ptr(), indices.data_ptr())
+        self.pattern_key = pattern_key if pattern_key is not None else new_pattern_id()
         self.coords = coords          # optional callable -> device (n, 2) DOF locations (locality key)
         self.candidates = candidates  # optional callable -> device (n, k) near-nullspace vectors (smoothed aggregation)
         self._spmv_plan = None
@@ -74,7 +83,8 @@ class DeviceCSR:
 
     # -- arithmetic that stays on the device -------------------------------------------------------
     def _same_pattern(self, other):
-        return isinstance(other, DeviceCSR) and other.pattern_key == self.pattern_key
+        return (isinstance(other, DeviceCSR) and other.pattern_key == self.pattern_key and other.shape == self.shape
+                and other.nnz == self.nnz)
 
     def _axpby(self, alpha, other, beta):
         torch = L.require_cuda()
@@ -225,7 +235,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
                                              L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']),
                                              L.ptr(pat['slot8']), L.ptr(pat['indptr']), L.ptr(vals), st),
                 'mwx_assemble_morley_mass')
-        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords,
+        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), pat['key'], coords=ubasis.dof_coords,
                       candidates=ubasis.nullspace_candidates)
         return K if f.terms['mass'] == 1.0 else f.terms['mass'] * K
     if f.kind == 'lagrange':
@@ -236,7 +246,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
         L.check(lib.mwx_assemble_lagrange_laplace(ubasis.N, m.nt, ubasis.Nbfun, L.ptr(m.d_pxy), L.ptr(m.d_t),
                                                   L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']),
                                                   L.ptr(pat['indptr']), L.ptr(vals), st), 'mwx_assemble_lagrange_laplace')
-        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords,
+        K = DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), pat['key'], coords=ubasis.dof_coords,
                       candidates=ubasis.constant_candidates)
         scale = f.terms['laplace']
         K = K if scale == 1.0 else scale * K
@@ -257,7 +267,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
                                          L.ptr(pat['indices']), t.get('penalty_1', 0.0), t.get('penalty_2', 0.0),
                                          t.get('penalty_3', 0.0), float(sigma), L.ptr(vals), st),
                 'mwx_assemble_penalty')
-        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ib.N, ib.N), coords=ib.dof_coords,
+        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ib.N, ib.N), pat['key'], coords=ib.dof_coords,
                          candidates=ib.nullspace_candidates)
     if not isinstance(ubasis, InteriorBasis):
         raise TypeError("asm_gpu expects an InteriorBasis or FacetBasis of this package")
@@ -271,7 +281,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
                                     L.ptr(pat['indptr']), f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0),
                                     1 if (accumulate and out is not None) else 0, L.ptr(vals), st),
             'mwx_assemble_morley')
-    return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), coords=ubasis.dof_coords,
+    return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), pat['key'], coords=ubasis.dof_coords,
                      candidates=ubasis.nullspace_candidates)
 
 
@@ -323,4 +333,6 @@ def project(fun, basis_to):
     M = asm_gpu(mass, basis_to)
     f = asm_gpu(LinearFormGPU(lambda v, w: fun(w.x[0], w.x[1]) * v), basis_to)
     x, its, info, resid = pcg(M, f, tol=1e-14, maxiter=20000, precondition=True)
+    if info != 0:
+        raise L.MwxError(f"project: the mass-matrix solve did not converge (info={info}, residual {resid:.3e})")
     return x.cpu().numpy()

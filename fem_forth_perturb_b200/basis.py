@@ -90,7 +90,8 @@ class InteriorBasis:
             # 64-byte element geometry records (Morley kernel only)
             exy = torch.empty(8 * m.nt if isinstance(self.elem, ElementTriMorley) else 8, dtype=torch.float64,
                               device=m.device)
-            self._pattern = dict(r2e_ptr=r2e_ptr, r2e_idx=r2e_idx, indptr=indptr, indices=indices, slot8=slot8, exy=exy,
+            from .assembly import new_pattern_id
+            self._pattern = dict(key=new_pattern_id(), r2e_ptr=r2e_ptr, r2e_idx=r2e_idx, indptr=indptr, indices=indices, slot8=slot8, exy=exy,
                                  nnz=int(nnz.value), max_row=int(maxrow.value))
         return self._pattern
 

@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                 if (valid && sub == 0) finish(r, sum);
             }
         }
+        // The products were written back INTO the TMA stage through the generic proxy: every writing thread orders
+        // its own stores before the async-proxy refill (PTX memory model: the fence must come from the writers, a
+        // barrier plus thread 0's fence alone is not enough), then the barrier hands the stage back to the producer.
+        if (nst >= 0) fence_proxy_async();
         __syncthreads();                 // stage fully consumed before thread 0 refills it next iteration
     }
     if (DOT) {

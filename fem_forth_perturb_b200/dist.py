@@ -369,6 +369,15 @@ class SymmMemComm(TorchDistComm):
         self.handles[t.data_ptr()] = (hdl, t)
         return t[:op.ncol + op.nghost]
 
+    def release(self, vecs):
+        """Forget symmetric-memory vectors handed out by ext_zeros (their handles and cached push plans)."""
+        for v in vecs:
+            ptr_ = v.data_ptr()
+            self.handles.pop(ptr_, None)
+            self.last_halo.pop(ptr_, None)
+            for k in [k for k in self._plans if k[1] == ptr_]:
+                del self._plans[k]
+
     def exchange_requests(self, parts):
         import torch
         super().exchange_requests(parts)
@@ -515,15 +524,21 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
     precond: 'jacobi' | 'none' | 'amg'; amg = a :class:`DistAMG` (global hierarchy, collective V-cycle) or a list of
     per-part AMGHierarchy objects (block-Jacobi: each rank preconditions with its own diagonal block).
     Returns (x_list, iters, info, resid)."""
-    ops = ops or CudaOps()
+    ops = ops or _default_ops()
     n_global = parts[0].partition.n
     if maxiter is None or maxiter <= 0:
         maxiter = 10 * n_global
-    # Per-part CG state.  It is cached on the parts (keyed by communicator / preconditioner) so that repeated solves
-    # reuse the symmetric-memory vectors.
-    key = (id(comm), precond, id(amg), id(ops))
+    # Per-part CG state.  It is cached on the parts so that repeated solves reuse the symmetric-memory vectors (a miss
+    # allocates and rendezvouses new ones).  The entry holds STRONG references to the communicator / preconditioner /
+    # kernel set it was built for and is matched by identity against them, so a recycled id() can never alias it.
+    key = (comm, precond, amg, ops)
     cache = getattr(parts[0], '_cg_state', None)
-    if cache is None or cache['key'] != key or len(cache['S']) != len(parts):
+    same = cache is not None and len(cache['S']) == len(parts) and cache['key'][1] == precond and all(
+        a is b for a, b in zip((cache['key'][0], cache['key'][2], cache['key'][3]), (comm, amg, ops)))
+    if not same:
+        if cache is not None and hasattr(cache['key'][0], 'release'):
+            for st in cache['S']:
+                cache['key'][0].release([st['x'], st['p']])
         S = []
         for p, b in zip(parts, b_list):
             dev = b.device
@@ -566,7 +581,8 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
     for p, st in zip(parts, S):
         ops.dot(p.nloc, st['b'], st['b'], st['ws'], SLOT_AUX)
     bnrm = math.sqrt(float(reduce_slots([SLOT_AUX])[0]))
-    xs = lambda: [st['x'][:p.nloc] for p, st in zip(parts, S)]
+    # the iterate lives in the cached state: hand out copies, or the next solve would overwrite a returned solution
+    xs = lambda: [st['x'][:p.nloc].clone() for p, st in zip(parts, S)]
     if bnrm <= tol:
         return xs(), 0, 0, bnrm
     atol = tol * bnrm if bnrm != 0.0 else tol
@@ -624,7 +640,7 @@ class PartitionedProblem:
         torch = L.require_cuda()
         pat = basis.pattern()
         proto = DeviceCSR(pat['indptr'], pat['indices'], torch.empty(0, dtype=torch.float64, device=basis.mesh.device),
-                          (basis.N, basis.N), coords=basis.dof_coords)
+                          (basis.N, basis.N), pat['key'], coords=basis.dof_coords)
         self.cplan = CondensePlan(proto, D=D)
         I_dev = torch.from_numpy(np.ascontiguousarray(self.cplan.I, dtype=np.int64)).to(basis.mesh.device)
         self.partition = Partition(basis.dof_coords()[I_dev], comm.world)

@@ -18,7 +18,7 @@ import warnings
 import numpy as np
 
 from . import _lib as L
-from .assembly import DeviceCSR
+from .assembly import DeviceCSR, new_pattern_id
 
 
 # ------------------------------------------------------------------ helpers
@@ -104,7 +104,7 @@ class Reordering:
             else:
                 vals = out[2] if out is not None else torch.empty(A.nnz, dtype=torch.float64, device=dev)
             _gather_values(A.d_data, ent['vmap'], vals)
-            return DeviceCSR(ent['indptr'], ent['indices'], vals, A.shape, **meta)
+            return DeviceCSR(ent['indptr'], ent['indices'], vals, A.shape, ent['key'], **meta)
         if out is None:
             out = (torch.empty(self.n + 1, dtype=torch.int64, device=dev),
                    torch.empty(A.nnz, dtype=torch.int32, device=dev),
@@ -112,10 +112,9 @@ class Reordering:
         L.check(L.lib().mwx_csr_permute(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data),
                                         L.ptr(self.perm), L.ptr(self.iperm), L.ptr(out[0]), L.ptr(out[1]),
                                         L.ptr(out[2]), L.stream()), 'mwx_csr_permute')
-        # keep the pattern tensors of the source alive with the entry: the key is made of their addresses
-        patterns[key] = dict(indptr=out[0].clone(), indices=out[1].clone(), vmap=None, scratch=None,
-                             source=(A.d_indptr, A.d_indices))
-        return DeviceCSR(out[0], out[1], out[2], A.shape, **meta)
+        ent = patterns[key] = dict(indptr=out[0].clone(), indices=out[1].clone(), vmap=None, scratch=None,
+                                   key=new_pattern_id())
+        return DeviceCSR(out[0], out[1], out[2], A.shape, ent['key'], **meta)
 
     def _gather(self, v, idx):
         torch = L.require_cuda()
@@ -501,10 +500,13 @@ class CondensePlan:
         if I is None:
             keep_h[:] = 1
             keep_h[D] = 0
-            I = np.nonzero(keep_h)[0]
         else:
-            keep_h[I] = 1
-        self.I, self.n, self.pattern_key = I, n, A.pattern_key
+            # The kernels keep rows in ascending DOF order.  The reference's A[I].T[I].T follows the order of I; every
+            # call site passes sorted, duplicate-free sets, so I is normalised here and the normalised set is what
+            # condense() returns (an unsorted I would otherwise scatter the solution to the wrong DOFs in solve()).
+            keep_h[np.asarray(I, dtype=np.int64)] = 1
+        I = np.nonzero(keep_h)[0]
+        self.I, self.n, self.pattern_key, self.out_key = I, n, A.pattern_key, new_pattern_id()
         self._I_dev = None
         dev = A.d_data.device
         self.keep = torch.from_numpy(keep_h).to(dev)
@@ -543,7 +545,7 @@ class CondensePlan:
                 del ids, tmp
             if self._vmap is not None:
                 _gather_values(A.d_data, self._vmap, vals)
-                return DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out),
+                return DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out), self.out_key,
                                  coords=self._rows_of(A, 'coords', dev),
                                  candidates=self._rows_of(A, 'candidates', dev)), None
         bd = _to_device_vec(b, dev) if have_b else None
@@ -553,7 +555,7 @@ class CondensePlan:
                                           L.ptr(self.keep), L.ptr(self.newid), L.ptr(self.indptr_out),
                                           L.ptr(self.indices_out), L.ptr(vals), L.ptr(bd), L.ptr(xd), L.ptr(b_out),
                                           L.stream()), 'mwx_condense_fill')
-        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out),
+        Aout = DeviceCSR(self.indptr_out, self.indices_out, vals, (self.n_out, self.n_out), self.out_key,
                          coords=self._rows_of(A, 'coords', dev), candidates=self._rows_of(A, 'candidates', dev))
         return Aout, b_out
 
@@ -573,7 +575,8 @@ class CondensePlan:
 
 def condense(A, b=None, x=None, I=None, D=None, expand=True):
     """ref utils.py:384-460 on the device: ``Aout = A[I].T[I].T``, ``bout = b[I] - A[I].T[D].T @ x[D]``.
-    ``A`` may be a DeviceCSR (stays in HBM) or a scipy matrix (uploaded)."""
+    ``A`` may be a DeviceCSR (stays in HBM) or a scipy matrix (uploaded).  Divergence from the reference: a given
+    ``I`` is normalised to ascending, duplicate-free order (``np.unique``) and that normalised set is returned."""
     D, I = _flatten_dofs(D), _flatten_dofs(I)
     A = _to_device_csr(A)
     if b is not None and not isinstance(b, np.ndarray) and not hasattr(b, 'data_ptr'):
