@@ -175,6 +175,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-rs-compare', action='store_true',
                     help="skip the one untimed solve on the reference's Ruge-Stueben hierarchy that mode 'sa' reports beside itself")
+    ap.add_argument('--no-ex1', action='store_true', help='skip the real example-1 problem (error norms vs the exact solution)')
+    ap.add_argument('--no-same-config', action='store_true', help="skip the level-8 pass in the reference's own mode")
+    ap.add_argument('--tight-tol', type=float, default=1e-10,
+                    help='second tolerance of the ex1 check: where both hierarchies have converged, their solutions must agree')
+    ap.add_argument('--asm-levels', type=int, nargs='*', default=[11, 13],
+                    help='extra levels of the assembly-only microbench reported in the line (the main level is timed in the step)')
     ap.add_argument('--microbench', action='store_true',
                     help='assembly-only microbench on the 2k/4k/8k meshes (levels 11, 12, 13), 1 GPU')
     args = ap.parse_args()
@@ -204,8 +210,107 @@ def main():
         run_microbench(args, torch, F)
         return
 
-    def sync_all():                                 # N = 1 here (N > 1 runs run_partitioned): no barrier needed
+    run_single(args, torch, F, L, dev, local)
+
+
+def kernel_traffic(kernel, level):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by profiles/ncu_summary.py).  An entry is keyed to the sha256 of the kernel's
+    source file at capture time: if the source has changed since, the number is stale and None is reported."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            ent = json.load(f).get(f'{kernel}@level{level}')
+        if not ent:
+            return None
+        with open(os.path.join(ROOT, ent['source']), 'rb') as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+        return ent['bytes'] if sha == ent['source_sha256'] else None
+    except Exception:
+        return None
+
+
+def ex1_pipeline(torch, F, gm, ubasis, plan, K2, eps, solve_u, w_mode, tol):
+    """The reference's solve_problem1 (ref main/example1/run.py:182-222, w in P1 as in the golden 8-level log) with
+    every array on the device: K1 = asm(laplace), f1 = asm(f_load) -> w_h; f2 = asm(wv_load) * w_h; condense; u_h.
+    Loads and the exact solution are the 'ex1' data of problems.py evaluated by the kernels.
+    solve_u: {name: callable(Kc, bc) -> (x, iters, info)}.  Returns per-solver error tables and iteration counts."""
+    prob = F.Problem('ex1', eps)
+    wb = F.InteriorBasis(gm, F.ElementTriP1(), intorder=5)
+    K1 = F.asm_gpu(F.laplace, wb)
+    f1 = F.asm_gpu(prob.f_load, wb, on_device=True)
+    planw = F.CondensePlan(K1, D=np.unique(wb.find_dofs()['all'].all()))
+    K1c, f1c = planw.apply(K1, f1)
+    t0 = time.perf_counter()
+    mlw = F.AMGHierarchy(K1c, mode=w_mode)
+    t_wsetup = time.perf_counter() - t0
+    xw, its_w, info_w, _ = F.pcg(K1c, f1c, tol, 2000, amg=mlw)
+    del mlw
+    wh = torch.zeros(wb.N, dtype=torch.float64, device=gm.device)
+    wh[torch.from_numpy(planw.I).to(gm.device)] = xw
+    f2 = F.asm_gpu(F.wv_load, wb, ubasis).dot(wh)
+    Kc, bc = plan.apply(K2, f2)
+    I_dev = torch.from_numpy(np.ascontiguousarray(plan.I, dtype=np.int64)).to(gm.device)
+    out = {'w_solve': {'iters': its_w, 'info': info_w, 'mode': w_mode, 'n': K1c.shape[0], 'amg_setup_s': t_wsetup}}
+    sols = {}
+    for name, fn in solve_u.items():
         torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x, its, info = fn(Kc, bc)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        uh = torch.zeros(ubasis.N, dtype=torch.float64, device=gm.device)
+        uh[I_dev] = x
+        L2, D1, D2 = F.morley_error_norms(ubasis, uh, problem=prob)
+        out[name] = {'iters': its, 'info': info, 's_per_solve': dt, 'L2': L2, 'H1': L2 + D1, 'H2': L2 + D1 + D2,
+                     'energy': float(np.sqrt(eps ** 2 * D2 ** 2 + D1 ** 2))}
+        sols[name] = x
+    return out, sols
+
+
+def same_config_level8(torch, F, L, level, tol):
+    """ONE pass timed exactly like cpu_reference_pass (same level, same phases, the reference's own preconditioner:
+    Ruge-Stueben hierarchy + symmetric Gauss-Seidel = mode 'parity', maxiter 1000, rhs = K2c @ U(-1,1) seed 1234)
+    on the device, so that the record holds one same-config GPU-vs-CPU pair."""
+    dev = torch.device('cuda', torch.cuda.current_device())
+    gm = F.MeshTri().refine(level)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ub = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+    K2 = F.asm_gpu(EPS ** 2 * F.a_load + F.b_load, ub)             # includes pattern + slot map (skfem: basis tabulation)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    bf = gm.boundary_facets()
+    D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+    Kc = F.condense(K2, D=D, expand=False)
+    xs = torch.from_numpy(np.random.default_rng(1234).uniform(-1, 1, Kc.shape[0])).to(dev)
+    b = Kc.dot(xs)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    y = Kc.dot(xs)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    ml = F.AMGHierarchy(Kc, mode='parity')
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
+    x, its, info, resid = F.pcg(Kc, b, tol, 1000, amg=ml)
+    torch.cuda.synchronize()
+    t5 = time.perf_counter()
+    step = (t1 - t0) + (t2 - t1) + (t3 - t2) + (t5 - t4)
+    return dict(level=level, ndofs=ub.N, n=Kc.shape[0], mode='parity (RS hierarchy + symmetric Gauss-Seidel, the reference\'s own)',
+                asm_s=t1 - t0, condense_s=t2 - t1, spmv_s=t3 - t2, amg_setup_s=t4 - t3, pcg_s=t5 - t4, iters=its, info=info,
+                value_mdof_s=ub.N / step / 1e6, value_incl_amg_setup_mdof_s=ub.N / (step + t4 - t3) / 1e6,
+                pcg_ms_per_iter=(t5 - t4) / max(its, 1) * 1e3,
+                rel_err_vs_manufactured=float(torch.linalg.norm(x - xs) / torch.linalg.norm(xs)),
+                timing='host wall clock around synchronised phases, one cold pass - exactly as the CPU arm is timed')
+
+
+def run_single(args, torch, F, L, dev, local):
+    rank = 0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    form = EPS ** 2 * F.a_load + F.b_load
+    spec_mode = 'chebyshev'                          # north_star (3): pyamg hierarchy built on the host, Chebyshev smoothing
+    modes = [args.mode] + ([spec_mode] if args.mode != spec_mode and not args.no_rs_compare else [])
 
     # ---------------------------------------------------------------- setup (timed, not part of a step)
     t0 = time.perf_counter()
@@ -218,7 +323,6 @@ def main():
     torch.cuda.synchronize()
     t_pattern = time.perf_counter() - t0
     N, nt, nnz = basis.N, gm.nt, pat['nnz']
-    form = EPS ** 2 * F.a_load + F.b_load
     # Dirichlet set of easy_boundary (ref main/example1/run.py:86-104): boundary vertices + boundary facets
     bf = gm.boundary_facets()
     D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
@@ -232,9 +336,11 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xstar = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 2 - 1     # manufactured solution
     b = Kc.dot(xstar)
-    t0 = time.perf_counter()
-    ml = F.AMGHierarchy(Kc, mode=args.mode)
-    t_amg = time.perf_counter() - t0
+    mls, t_amg = {}, {}
+    for mode in modes:
+        t0 = time.perf_counter()
+        mls[mode] = F.AMGHierarchy(Kc, mode=mode)
+        t_amg[mode] = time.perf_counter() - t0
     # pinned host inputs / outputs for the end-to-end leg
     p_host = torch.empty(2 * gm.nv, dtype=torch.float64).pin_memory()
     t_host = torch.empty(3 * gm.nt, dtype=torch.int32).pin_memory()
@@ -245,17 +351,14 @@ def main():
     vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     vals_c = torch.empty(nnzc, dtype=torch.float64, device=dev)
     ysp = torch.empty(n, dtype=torch.float64, device=dev)
-    perm_bufs = None
-    if ml.reordering is not None:                       # solver-side copy P K2c P^T, refreshed every step
-        perm_bufs = (torch.empty(n + 1, dtype=torch.int64, device=dev), torch.empty(nnzc, dtype=torch.int32, device=dev),
-                     torch.empty(nnzc, dtype=torch.float64, device=dev))
+    perm_bufs = (torch.empty(n + 1, dtype=torch.int64, device=dev), torch.empty(nnzc, dtype=torch.int32, device=dev),
+                 torch.empty(nnzc, dtype=torch.float64, device=dev))           # solver-side copy P K2c P^T, refreshed every step
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)     # 256 MiB > 126 MB L2
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
     hints = {}
 
-    def step(e2e):
+    def step(e2e, mode):
         """One pass of the hot path.  Returns per-phase device milliseconds and the iteration count."""
+        ml = mls[mode]
         marks = [ev() for _ in range(8)]
         if e2e:
             gm.d_pxy.copy_(p_host, non_blocking=True)
@@ -278,10 +381,9 @@ def main():
         Ks = ml.reordering.matrix(Kcs, out=perm_bufs) if ml.reordering is not None else Kcs
         if 'ks' not in hints:
             hints['ks'] = Ks.spmv_hint()
-        ks_hint = hints['ks']
         flush.zero_()
         marks[5].record()
-        L.check(L.lib().mwx_spmv(n, ks_hint, L.ptr(Ks.d_indptr), L.ptr(Ks.d_indices), L.ptr(Ks.d_data), L.ptr(xstar),
+        L.check(L.lib().mwx_spmv(n, hints['ks'], L.ptr(Ks.d_indptr), L.ptr(Ks.d_indices), L.ptr(Ks.d_data), L.ptr(xstar),
                                  L.ptr(ysp), L.stream()), 'mwx_spmv')
         marks[6].record()
         x, its, info, resid = F.pcg(Kcs, bd, TOL, 2000, amg=ml)
@@ -293,53 +395,93 @@ def main():
         return dict(asm=ms[0], condense=ms[1], spmv_skfem=ms[3], reorder=ms[4], spmv=ms[5], pcg=ms[6], its=its,
                     info=info, resid=resid, x=x)
 
-    def timed(e2e, steps, warmup):
+    def timed(e2e, mode, steps, warmup):
         for _ in range(warmup):
-            step(e2e)
-        sync_all()
+            step(e2e, mode)
+        torch.cuda.synchronize()
         e0, e1 = ev(), ev()
         e0.record()
-        rs = [step(e2e) for _ in range(steps)]
+        rs = [step(e2e, mode) for _ in range(steps)]
         e1.record()
-        sync_all()
+        torch.cuda.synchronize()
         return e0.elapsed_time(e1), rs
 
+    def mean(key, rr):
+        return float(np.mean([r[key] for r in rr]))
+
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    total_ms, rs = timed(False, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_ms, rs_e2e = timed(True, args.steps, 1)
+    sampler.start()
+    total_ms, rs = timed(False, args.mode, args.steps, args.warmup)
+    clocks = sampler.stop()
+    e2e_ms, rs_e2e = timed(True, args.mode, args.steps, 1)
+    ms_step = total_ms / args.steps
+    value = N / (ms_step * 1e-3) / 1e6
+    xerr = float(torch.linalg.norm(rs[-1]['x'] - xstar) / torch.linalg.norm(xstar))
 
-    # mode 'sa' replaces the reference's hierarchy: report ONE solve of the same system on the reference's Ruge-Stueben
-    # hierarchy (same device V-cycle and Chebyshev smoother) beside it - outside the timed steps
-    rs_compare = None
-    if args.mode == 'sa' and not args.no_rs_compare and args.level <= 12:
+    def mode_block(mode, ms_step_, e2e_ms_step, rr):
+        ml = mls[mode]
+        its = rr[-1]['its']
+        setup = t_amg[mode]
+        return {'hierarchy': ('smoothed aggregation on the Morley interpolants of 1, x, y (no reference counterpart)' if mode == 'sa'
+                              else "pyamg ruge_stuben_solver defaults (the reference's hierarchy; C++ host restatement)"),
+                'smoother': 'symmetric Gauss-Seidel (pyamg default)' if mode == 'parity' else ('2x damped Jacobi' if mode == 'jacobi' else 'Chebyshev(2)'),
+                'value_mdof_s': N / (ms_step_ * 1e-3) / 1e6, 'ms_per_step': ms_step_,
+                'e2e_mdof_s': None if e2e_ms_step is None else N / (e2e_ms_step * 1e-3) / 1e6,
+                'value_incl_amg_setup_mdof_s': N / (ms_step_ * 1e-3 + setup) / 1e6,
+                'pcg_iters': its, 'pcg_info': rr[-1]['info'], 'pcg_s_per_solve': mean('pcg', rr) * 1e-3,
+                'pcg_ms_per_iter': mean('pcg', rr) / max(its, 1),
+                'amg_setup_s': setup, 'amg_host_setup_s': ml.setup_host_seconds, 'amg_upload_s': ml.upload_seconds,
+                'amg_reorder_s': ml.reorder_seconds, 'levels': ml.level_sizes(),
+                'operator_complexity': ml.operator_complexity(),
+                'rel_err_vs_manufactured': float(torch.linalg.norm(rr[-1]['x'] - xstar) / torch.linalg.norm(xstar))}
+
+    by_mode = {args.mode: mode_block(args.mode, ms_step, e2e_ms / args.steps, rs)}
+    x_by_mode = {args.mode: rs[-1]['x']}
+    for mode in modes[1:]:                             # the spec mode beside it: same step function, fewer steps
         try:
-            t0 = time.perf_counter()
-            ml_rs = F.AMGHierarchy(Kc, mode='chebyshev')
-            t_rs_setup = time.perf_counter() - t0
-            e0, e1 = ev(), ev()
-            torch.cuda.synchronize()
-            e0.record()
-            x_rs, its_rs, info_rs, _ = F.pcg(Kc, b, TOL, 2000, amg=ml_rs)
-            e1.record()
-            torch.cuda.synchronize()
-            rs_compare = {'hierarchy': 'pyamg ruge_stuben_solver defaults (C++ host restatement), Chebyshev(2) smoothing',
-                          'iters': its_rs, 'info': info_rs, 's_per_solve': e0.elapsed_time(e1) * 1e-3,
-                          'levels': ml_rs.level_sizes(), 'operator_complexity': ml_rs.operator_complexity(),
-                          'amg_host_setup_s': ml_rs.setup_host_seconds, 'amg_total_setup_s': t_rs_setup,
-                          'rel_err_vs_manufactured': float(torch.linalg.norm(x_rs - xstar) / torch.linalg.norm(xstar)),
-                          'rel_diff_to_sa_solution': float(torch.linalg.norm(x_rs - rs[-1]['x']) / torch.linalg.norm(x_rs)),
-                          'note': 'both solves stop on the same residual criterion (scipy 1.4.1, tol 1e-8); the operator is '
-                                  'ill-conditioned (eps^2/h^2 ~ 1.7e3), so the forward errors w.r.t. the manufactured x* differ'}
-            del ml_rs, x_rs
-            torch.cuda.empty_cache()
-        except Exception as exc:                      # never let the side measurement take the bench line down
-            rs_compare = {'error': repr(exc)[:300]}
+            k = max(1, min(2, args.steps))
+            tms, rr = timed(False, mode, k, 1)
+            by_mode[mode] = mode_block(mode, tms / k, None, rr)
+            by_mode[mode]['steps'] = k
+            x_by_mode[mode] = rr[-1]['x']
+        except Exception as exc:                        # never let the side measurement take the bench line down
+            by_mode[mode] = {'error': repr(exc)[:300]}
+    if len(x_by_mode) == 2:
+        xa, xb = x_by_mode[modes[0]], x_by_mode[modes[1]]
+        by_mode['rel_diff_between_modes_tol1e-8_manufactured_rhs'] = float(torch.linalg.norm(xa - xb) / torch.linalg.norm(xb))
+    del x_by_mode
 
-    # the same assembly on the Hilbert-renumbered copy of the mesh (MeshTri.renumbered(): same triangles, vertex and
-    # element numbers follow a space-filling curve) - outside the timed steps, reported beside the default order
+    # ---------------------------------------------------------------- the real example-1 problem at this level (and one below)
+    ex1 = None
+    if not args.no_ex1:
+        ex1 = {'what': "ref main/example1/run.py solve_problem1 (w in P1, eps = %g, tol = %g) on the device; errors vs the exact "
+                       "solution u = (sin pi x sin pi y)^2; H1 = L2 + |.|_1h, H2 = H1 + |.|_2h, energy = sqrt(eps^2 |.|_2h^2 + |.|_1h^2) "
+                       "as the reference prints them (run.py:519-543)" % (EPS, TOL), 'levels': {}}
+        try:
+            def solver(mode, tol, ml_by_mode):
+                def fn(Kc_, bc_):
+                    x, its, info, _ = F.pcg(Kc_, bc_, tol, 600, amg=ml_by_mode[mode])
+                    return x, its, info
+                return fn
+            tight = args.tight_tol
+            solve_u = {}
+            for mode in modes:
+                solve_u[f'{mode}_tol{TOL:g}'] = solver(mode, TOL, mls)
+            for mode in modes:
+                solve_u[f'{mode}_tol{tight:g}'] = solver(mode, tight, mls)
+            res, sols = ex1_pipeline(torch, F, gm, basis, plan, K2, EPS, solve_u, args.mode if args.mode in ('sa', 'chebyshev') else 'chebyshev', TOL)
+            if len(modes) == 2:
+                for tol in (TOL, tight):
+                    a, b2 = sols[f'{modes[0]}_tol{tol:g}'], sols[f'{modes[1]}_tol{tol:g}']
+                    res[f'rel_l2_diff_{modes[0]}_vs_{modes[1]}_tol{tol:g}'] = float(torch.linalg.norm(a - b2) / torch.linalg.norm(b2))
+            ex1['levels'][str(args.level)] = res
+            del sols
+        except Exception as exc:
+            ex1['levels'][str(args.level)] = {'error': repr(exc)[:300]}
+        solve_u = solver = None                      # the closures hold the hierarchies
+
+    # free the big level before the side measurements
+    same_cfg = None
     asm_renum_ms = None
     if args.level <= 12:
         gm2 = gm.renumbered()
@@ -358,62 +500,105 @@ def main():
         del K2r, basis2, gm2
         torch.cuda.empty_cache()
 
-    # solution check of the last solve (manufactured x*)
-    xerr = float(torch.linalg.norm(rs[-1]['x'] - xstar) / torch.linalg.norm(xstar))
-
-    def mean(key, rr=rs):
-        return float(np.mean([r[key] for r in rr]))
-
     peak, peak_src = measured_peaks()
-    ms_step = total_ms / args.steps
-    units = N
-    value = units / (ms_step * 1e-3) / 1e6
     spmv_bytes = 12 * nnzc + 20 * n                            # values 8 + col 4 per nnz; 20 B/row
     asm_bytes = 308 * nt                                       # DESIGN.md section 4 (gather formulation)
-    spmv_gbs = spmv_bytes / (mean('spmv') * 1e-3) / 1e9
-    asm_gbs = asm_bytes / (mean('asm') * 1e-3) / 1e9
+    spmv_gbs = spmv_bytes / (mean('spmv', rs) * 1e-3) / 1e9
+    asm_gbs = asm_bytes / (mean('asm', rs) * 1e-3) / 1e9
     iters = rs[-1]['its']
-    # kernels launched per step (counted from the code paths above): assembly 1; condense 2 scans (3+3+..) + 2;
-    # spmv 1; PCG: per iteration 3 CG kernels + dot + V-cycle kernels
+    ml = mls[args.mode]
     nlev = ml.levels
     per_vcycle = (nlev - 1) * 7 + 1      # per level: first step, 1 smoother SpMV, residual, restrict, prolong, 2 smoother SpMVs; + coarse gemv
-    gpu_launches = int(args.steps * (1 + 1 + 1 + 1 + 3 + iters * (4 + per_vcycle)))
+    gpu_launches = int(args.steps * (2 + 1 + 1 + 1 + 3 + iters * (4 + per_vcycle)))
+    level_main = args.level
+    numbering = 'hilbert (solver-internal)' if ml.reordering is not None else 'skfem'
+
+    # release the level-L objects, then the smaller side blocks
+    del ml, mls, K2, Kc, plan, basis, pat, gm, vals, vals_c, perm_bufs, ysp, xstar, b, rs_e2e
+    for r in rs:
+        r.pop('x', None)
+    torch.cuda.empty_cache()
+    if ex1 is not None and args.level >= 9:
+        lvl = args.level - 1
+        try:
+            gm1 = F.MeshTri().refine(lvl)
+            ub1 = F.InteriorBasis(gm1, F.ElementTriMorley(), intorder=5)
+            bf1 = gm1.boundary_facets()
+            D1 = np.concatenate((np.unique(gm1.facets[:, bf1]), bf1 + gm1.nv))
+            K21 = F.asm_gpu(form, ub1)
+            plan1 = F.CondensePlan(K21, D=D1)
+            Kc1, _ = plan1.apply(K21)
+            mls1 = {mode: F.AMGHierarchy(Kc1, mode=mode) for mode in modes}
+            solve_u = {f'{mode}_tol{TOL:g}': (lambda Kc_, bc_, mode=mode: F.pcg(Kc_, bc_, TOL, 600, amg=mls1[mode])[:3]) for mode in modes}
+            res, sols = ex1_pipeline(torch, F, gm1, ub1, plan1, K21, EPS, solve_u, args.mode if args.mode in ('sa', 'chebyshev') else 'chebyshev', TOL)
+            ex1['levels'][str(lvl)] = res
+            hi = ex1['levels'].get(str(args.level), {})
+            for name in solve_u:                        # convergence orders level L-1 -> L (reference table: ~2 / 2 / 1 / 2 ... )
+                if name in hi and name in res:
+                    hi[name]['orders_vs_level_below'] = {k: float(-np.log2(hi[name][k] / res[name][k])) for k in ('L2', 'H1', 'H2', 'energy')}
+            del sols, mls1, Kc1, plan1, K21, ub1, gm1
+        except Exception as exc:
+            ex1['levels'][str(lvl)] = {'error': repr(exc)[:300]}
+        torch.cuda.empty_cache()
+    if not args.no_same_config:
+        try:
+            same_cfg = {'gpu': same_config_level8(torch, F, L, args.ref_level, TOL)}
+        except Exception as exc:
+            same_cfg = {'gpu': {'error': repr(exc)[:300]}}
+        torch.cuda.empty_cache()
+    micro = None
+    if args.asm_levels:
+        micro = []
+        for lvl in args.asm_levels:
+            try:
+                micro.append(assembly_only(torch, F, lvl, peak))
+            except Exception as exc:
+                micro.append({'level': lvl, 'error': repr(exc)[:200]})
+            torch.cuda.empty_cache()
+
+    main_mode = by_mode[args.mode]
     line = {
-        'metric': 'hot_path_MDOF_per_s', 'value': value, 'unit': 'MDOF/s', 'n_gpus': world, 'steps': args.steps,
+        'metric': 'hot_path_MDOF_per_s', 'value': value, 'unit': 'MDOF/s', 'n_gpus': 1, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'MWX assemble+condense+SpMV+AMG-PCG, unit square level {args.level}: {N} Morley DOFs, '
+        'value_mode': args.mode,
+        'value_incl_amg_setup': main_mode['value_incl_amg_setup_mdof_s'],
+        'value_spec_mode': by_mode.get(spec_mode, {}).get('value_mdof_s'),
+        'value_spec_mode_incl_amg_setup': by_mode.get(spec_mode, {}).get('value_incl_amg_setup_mdof_s'),
+        'config': {'workload': f'MWX assemble+condense+SpMV+AMG-PCG, unit square level {level_main}: {N} Morley DOFs, '
                                f'{nt} triangles, nnz(K2)={nnz}, condensed n={n}; eps={EPS}, tol={TOL}, rhs=K2c@x* '
-                               f'(x*~U(-1,1), seed 1234); AMG mode={args.mode} ' + ('(smoothed aggregation on the Morley interpolants of 1,x,y; Chebyshev(2) smoothing)' if args.mode == 'sa' else '(reference Ruge-Stueben hierarchy)'),
+                               f'(x*~U(-1,1), seed 1234); `value` = AMG mode {args.mode!r}; the spec mode '
+                               f'(reference RS hierarchy + Chebyshev) is timed beside it in `modes`/`value_spec_mode`',
                    'l2': 'operator (9.3 GB) and vectors (0.5 GB each) exceed the 126 MB L2; a 256 MiB buffer is '
                          'written before the SpMV sample'},
-        'assembly_mdof_s': N / (mean('asm') * 1e-3) / 1e6,
-        'assembly_ms': mean('asm'), 'condense_ms': mean('condense'),
-        'pcg': {'s_per_solve': mean('pcg') * 1e-3, 'iters': iters, 'info': rs[-1]['info'], 'mode': args.mode,
-                'ms_per_iter': mean('pcg') / max(iters, 1), 'rel_err_vs_manufactured': xerr,
-                'levels': ml.level_sizes(), 'operator_complexity': ml.operator_complexity(),
-                'reference_hierarchy': rs_compare},
-        'spmv': {'ms': mean('spmv'), 'gbs': spmv_gbs, 'frac_of_peak': spmv_gbs / peak,
-                 'numbering': 'hilbert (solver-internal)' if ml.reordering is not None else 'skfem',
-                 'skfem_numbering_ms': mean('spmv_skfem'),
-                 'skfem_numbering_gbs': spmv_bytes / (mean('spmv_skfem') * 1e-3) / 1e9},
-        'reorder_ms': mean('reorder'),
-        'setup_s': {'mesh_refine': t_mesh, 'pattern_slotmap': t_pattern, 'condense_plan': t_cplan, 'amg_host_rs': ml.setup_host_seconds,
-                    'amg_upload': ml.upload_seconds, 'amg_reorder': ml.reorder_seconds, 'amg_total': t_amg},
+        'modes': by_mode,
+        'assembly_mdof_s': N / (mean('asm', rs) * 1e-3) / 1e6,
+        'assembly_ms': mean('asm', rs), 'condense_ms': mean('condense', rs),
+        'pcg': {'s_per_solve': mean('pcg', rs) * 1e-3, 'iters': iters, 'info': rs[-1]['info'], 'mode': args.mode,
+                'ms_per_iter': mean('pcg', rs) / max(iters, 1), 'rel_err_vs_manufactured': xerr},
+        'spmv': {'ms': mean('spmv', rs), 'gbs': spmv_gbs, 'frac_of_peak': spmv_gbs / peak,
+                 'numbering': numbering,
+                 'skfem_numbering_ms': mean('spmv_skfem', rs),
+                 'skfem_numbering_gbs': spmv_bytes / (mean('spmv_skfem', rs) * 1e-3) / 1e9},
+        'reorder_ms': mean('reorder', rs),
+        'setup_s': {'mesh_refine': t_mesh, 'pattern_slotmap': t_pattern, 'condense_plan': t_cplan,
+                    'amg_total': t_amg[args.mode], 'amg_total_by_mode': t_amg},
         'roofline': {'kernel': 'k_spmv (CSR SpMV, fine level, solver numbering)', 'bound': 'hbm', 'achieved': spmv_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': spmv_gbs / peak,
-                     'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_spmv'), 'peak_source': peak_src,
+                     'traffic': kernel_traffic('k_spmv', level_main), 'peak_source': peak_src,
                      'algorithmic_bytes': spmv_bytes},
-        'roofline_assembly': {'kernel': 'k_element_geometry + k_assemble_morley_persistent', 'bound': 'hbm', 'achieved': asm_gbs,
+        'roofline_assembly': {'kernel': F.assembly_kernel_name(), 'bound': 'hbm', 'achieved': asm_gbs,
                               'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
-                              'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_assemble_morley'),
+                              'traffic': kernel_traffic('assembly', level_main),
                               'algorithmic_bytes': asm_bytes,
                               'renumbered_mesh': None if asm_renum_ms is None else {
                                   'ms': asm_renum_ms, 'mdof_s': N / (asm_renum_ms * 1e-3) / 1e6,
                                   'achieved': asm_bytes / (asm_renum_ms * 1e-3) / 1e9,
-                                  'frac': asm_bytes / (asm_renum_ms * 1e-3) / 1e9 / peak,
-                                  'traffic': NCU_TRAFFIC_BYTES.get(args.level, {}).get('k_assemble_morley_renumbered')}},
-        'e2e': {'value': units / (e2e_ms / args.steps * 1e-3) / 1e6, 'unit': 'MDOF/s',
+                                  'frac': asm_bytes / (asm_renum_ms * 1e-3) / 1e9 / peak}},
+        'assembly_microbench': micro,
+        'ex1_check': ex1,
+        'same_config': same_cfg,
+        'e2e': {'value': N / (e2e_ms / args.steps * 1e-3) / 1e6, 'unit': 'MDOF/s',
                 'h2d_bytes_per_step': int(p_host.numel() * 8 + t_host.numel() * 4 + b_host.numel() * 8),
                 'd2h_bytes_per_step': int(x_host.numel() * 8), 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': gpu_launches,
@@ -432,7 +617,34 @@ def main():
             'spmv_gbs': (12 * r['nnz'] + 20 * r['n']) / r['spmv_s'] / 1e9,
             'pcg_ms_per_iter': r['pcg_s'] / max(r['iters'], 1) * 1e3,
             'host_cores_available': os.cpu_count(), 'wall_s': time.perf_counter() - t0}
+        if same_cfg is not None:
+            same_cfg['cpu'] = dict(level=args.ref_level, ndofs=r['ndofs'], n=r['n'], asm_s=r['asm_s'], condense_s=r['condense_s'],
+                                   spmv_s=r['spmv_s'], amg_setup_s=r['amg_setup_s'], pcg_s=r['pcg_s'], iters=r['iters'],
+                                   info=r['info'], value_mdof_s=r['ndofs'] / cpu_s / 1e6,
+                                   value_incl_amg_setup_mdof_s=r['ndofs'] / (cpu_s + r['amg_setup_s']) / 1e6,
+                                   pcg_ms_per_iter=r['pcg_s'] / max(r['iters'], 1) * 1e3, kind='oracle port, 1 core')
     print(json.dumps(line))
+
+
+def assembly_only(torch, F, level, peak):
+    """Assembly-only sample of one level (BASELINE config 'assembly-only microbench 2k x 2k - 8k x 8k')."""
+    gm = F.MeshTri().refine(level)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    form = EPS ** 2 * F.a_load + F.b_load
+    K = F.asm_gpu(form, basis)
+    for _ in range(3):
+        F.asm_gpu(form, basis, out=K.d_data)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        F.asm_gpu(form, basis, out=K.d_data)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    return {'level': level, 'squares': f'{2 ** level}x{2 ** level}', 'dofs': basis.N, 'nnz': K.nnz, 'assembly_ms': ms,
+            'gdof_s': basis.N / ms / 1e6, 'gbs_308B_per_element': 308 * gm.nt / ms / 1e6,
+            'frac_of_peak': 308 * gm.nt / ms / 1e6 / peak}
 
 
 def run_microbench(args, torch, F):

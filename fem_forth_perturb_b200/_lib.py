@@ -31,6 +31,8 @@ _SIGNATURES = {
     'mwx_pattern_fill': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
     'mwx_assemble_lagrange_laplace': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_load_vector': [i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_load_vector_problem': [i32, f64, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_morley_error_sums_problem': [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp],
     'mwx_wv_action': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_morley_error_sums': [i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_assemble_morley_mass': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],

@@ -183,14 +183,26 @@ class MixedAction:
         raise NotImplementedError("the mixed (Morley x Lagrange) matrix is applied, not stored; use `A * wh`")
 
 
-def asm_load(form, basis):
-    """``asm(LinearForm, basis)``: host-sampled integrand, device integration -> numpy vector (like skfem)."""
+def asm_load(form, basis, on_device=False):
+    """``asm(LinearForm, basis)``: host-sampled integrand, device integration -> numpy vector (like skfem).
+    ``on_device=True`` (forms of :mod:`problems` on a P1 / P2 basis): the load is evaluated by the kernel and the
+    result stays a device tensor - no nt*nq host samples."""
     torch = L.require_cuda()
     m, pat = basis.mesh, basis.pattern()
-    fq = torch.from_numpy(form.sample(basis)).to(m.device)
     out = torch.empty(basis.N, dtype=torch.float64, device=m.device)
     X, W = basis.quadrature()
     from .basis import ElementTriMorley
+    if on_device:
+        prob = getattr(form, 'device_problem', None)
+        if prob is None or isinstance(basis.elem, ElementTriMorley):
+            raise NotImplementedError("on_device=True needs a load from fem_forth_perturb_b200.problems on a P1 / P2 "
+                                      "basis; arbitrary Python integrands are sampled on the host")
+        L.check(L.lib().mwx_load_vector_problem(prob[0], prob[1], basis.N, m.nt, basis.Nbfun, len(W),
+                                                L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy), L.ptr(m.d_t),
+                                                L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(out), L.stream()),
+                'mwx_load_vector_problem')
+        return out
+    fq = torch.from_numpy(form.sample(basis)).to(m.device)
     if isinstance(basis.elem, ElementTriMorley):
         L.check(L.lib().mwx_morley_load_vector(basis.N, m.nt, len(W), L.ptr(basis.d_quadrature()), L.ptr(m.d_pxy),
                                                L.ptr(m.d_t), L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(fq),
@@ -202,7 +214,7 @@ def asm_load(form, basis):
     return out.cpu().numpy()
 
 
-def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
+def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False, on_device=False):
     """Assemble ``form`` on ``ubasis`` -> :class:`DeviceCSR` (``.tocsr()`` gives scipy's matrix).
 
     ``form``: a descriptor from :mod:`forms` (or a linear combination such as
@@ -216,7 +228,7 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
     from .forms import LinearFormGPU
     from .basis import ElementTriMorley
     if isinstance(form, LinearFormGPU):
-        return asm_load(form, ubasis)
+        return asm_load(form, ubasis, on_device=on_device)
     f = as_form(form)
     if f.kind == 'mixed':
         if vbasis is None or not isinstance(vbasis.elem, ElementTriMorley) or isinstance(ubasis.elem, ElementTriMorley):
@@ -288,12 +300,27 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False):
 asm = asm_gpu
 
 
-def morley_error_norms(basis, uh, exact_u, dexact_u, ddexact):
+def assembly_kernel_name():
+    """Name of the kernel(s) behind ``asm_gpu(eps**2 * a_load + b_load, basis)`` in this build (bench.py's roofline label)."""
+    return 'k_element_geometry + k_assemble_morley_persistent'
+
+
+def morley_error_norms(basis, uh, exact_u=None, dexact_u=None, ddexact=None, problem=None):
     """(L2, D1, D2) = (||u_h - u||_0, |u_h - u|_{1,h}, |u_h - u|_{2,h}) as ref main/example1/run.py:157-179,519-531
     (``L2uError``, ``get_DuError``, ``get_D2uError``): the exact solution is sampled at the quadrature points on
-    the host (it is a Python function), the element integrals and their sum run on the device."""
+    the host (it is a Python function), the element integrals and their sum run on the device.
+    ``problem`` = a :class:`problems.Problem`: its exact solution is evaluated by the kernel instead (no host samples)."""
     torch = L.require_cuda()
     m = basis.mesh
+    if problem is not None:
+        uhd = torch.from_numpy(np.ascontiguousarray(uh, dtype=np.float64)).to(m.device) if isinstance(uh, np.ndarray) else uh
+        sums = torch.empty(3, dtype=torch.float64, device=m.device)
+        _, W = basis.quadrature()
+        L.check(L.lib().mwx_morley_error_sums_problem(problem.device_problem[0], m.nt, len(W), L.ptr(basis.d_quadrature()),
+                                                      L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(basis.d_element_dofs), L.ptr(uhd),
+                                                      L.ptr(sums), L.stream()), 'mwx_morley_error_sums_problem')
+        s = np.sqrt(sums.cpu().numpy())
+        return float(s[0]), float(s[1]), float(s[2])
     x = basis.global_coordinates()
     u = exact_u(x[0], x[1])
     ux, uy = dexact_u(x[0], x[1])

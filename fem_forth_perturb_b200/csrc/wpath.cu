@@ -88,6 +88,56 @@ __global__ void __launch_bounds__(128) k_assemble_lagrange(int64_t nrows, int64_
     }
 }
 
+// ---- problem data evaluated on the device (optional: `problem` > 0 and no host samples).  The reference's loads and
+// exact solutions are Python closures (ref main/example1/run.py:275-309 'ex1', :466-493 'ex3'); sampling them on the
+// host is fine for the shipped ladders (<= 263 k DOFs) but not for a 33.5 M-triangle mesh (235 M points, 11 GB of
+// samples for the error norms), so the two problems the examples use are also available as device functions.
+//   problem 1 ('ex1'): u = (sin pi x sin pi y)^2,  f = eps^2 lap^2 u - lap u
+//   problem 3 ('ex3'): u = sin pi x sin pi y,      f = 2 pi^2 u   (the reference's 'ex3' load has no eps term)
+constexpr double kPi = 3.14159265358979323846;
+
+__device__ __forceinline__ double problem_load(int problem, double eps, double x, double y) {
+    double sx, cx, sy, cy;
+    sincospi(x, &sx, &cx);
+    sincospi(y, &sy, &cy);
+    if (problem == 1) {
+        const double c2x = cx * cx - sx * sx, c2y = cy * cy - sy * sy;             // cos(2 pi x), cos(2 pi y)
+        const double g = c2x * sy * sy + c2y * sx * sx;
+        const double lu = 2.0 * kPi * kPi * g;
+        const double llu = -8.0 * kPi * kPi * kPi * kPi * (g - c2x * c2y);
+        return eps * eps * llu - lu;
+    }
+    return 2.0 * kPi * kPi * sx * sy;
+}
+
+// out = {u, ux, uy, uxx, uxy, uyy}
+__device__ __forceinline__ void problem_exact(int problem, double x, double y, double out[6]) {
+    double sx, cx, sy, cy;
+    sincospi(x, &sx, &cx);
+    sincospi(y, &sy, &cy);
+    if (problem == 1) {
+        out[0] = sx * sx * sy * sy;
+        out[1] = 2.0 * kPi * cx * sx * sy * sy;
+        out[2] = 2.0 * kPi * cy * sy * sx * sx;
+        out[3] = 2.0 * kPi * kPi * (cx * cx - sx * sx) * sy * sy;
+        out[4] = 4.0 * kPi * kPi * cx * sx * cy * sy;
+        out[5] = 2.0 * kPi * kPi * (cy * cy - sy * sy) * sx * sx;
+    } else {
+        out[0] = sx * sy;
+        out[1] = kPi * cx * sy;
+        out[2] = kPi * cy * sx;
+        out[3] = -kPi * kPi * sx * sy;
+        out[4] = kPi * kPi * cx * cy;
+        out[5] = -kPi * kPi * sx * sy;
+    }
+}
+
+__device__ __forceinline__ double problem_exact_value(int problem, double x, double y) {
+    double u6[6];
+    problem_exact(problem, x, y, u6);
+    return u6[0];
+}
+
 // reference basis values at X = (xi, eta): lambda = (1 - xi - eta, xi, eta)
 __device__ __forceinline__ double lagrange_value(int ndpe, int l, double l0, double l1, double l2) {
     const double lam[3] = {l0, l1, l2};
@@ -102,7 +152,7 @@ __device__ __forceinline__ double lagrange_value(int ndpe, int l, double l0, dou
 __global__ void k_load_vector(int64_t nrows, int64_t nt, int ndpe, int nq, const double *__restrict__ XW,
                               const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
                               const int64_t *__restrict__ r2e_ptr, const int32_t *__restrict__ r2e_idx,
-                              const double *__restrict__ fq, double *__restrict__ out) {
+                              const double *__restrict__ fq, int problem, double eps, double *__restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
     double acc = 0.0;
@@ -115,7 +165,10 @@ __global__ void k_load_vector(int64_t nrows, int64_t nt, int ndpe, int nq, const
         double s = 0.0;
         for (int q = 0; q < nq; ++q) {
             const double xi = XW[q], eta = XW[nq + q], w = XW[2 * nq + q];
-            s += fq[e * nq + q] * lagrange_value(ndpe, l, 1.0 - xi - eta, xi, eta) * (adet * w);
+            const double f = fq ? fq[e * nq + q]
+                                : problem_load(problem, eps, x0.x + (x1.x - x0.x) * xi + (x2.x - x0.x) * eta,
+                                               x0.y + (x1.y - x0.y) * xi + (x2.y - x0.y) * eta);
+            s += f * lagrange_value(ndpe, l, 1.0 - xi - eta, xi, eta) * (adet * w);
         }
         acc += s;
     }
@@ -223,7 +276,7 @@ __global__ void __launch_bounds__(128) k_morley_errors(int64_t nt, int nq, const
                                                        const int32_t *__restrict__ t,
                                                        const int32_t *__restrict__ edofs,
                                                        const double *__restrict__ uh,
-                                                       const double *__restrict__ ex,
+                                                       const double *__restrict__ ex, int problem,
                                                        double *__restrict__ partials) {
     __shared__ double sh[32];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,8 +306,15 @@ __global__ void __launch_bounds__(128) k_morley_errors(int64_t nt, int nq, const
                 gx += u[i] * g.x; gy += u[i] * g.y;
             }
             const int64_t o = e * nq + q, N = nt * (int64_t)nq;
-            const double dv = val - ex[o], dgx = gx - ex[N + o], dgy = gy - ex[2 * N + o];
-            const double dxx = hxx - ex[3 * N + o], dxy = hxy - ex[4 * N + o], dyy = hyy - ex[5 * N + o];
+            double u6[6];
+            if (ex) {
+                for (int c = 0; c < 6; ++c) u6[c] = ex[c * N + o];
+            } else {
+                problem_exact(problem, x0.x + (x1.x - x0.x) * xi + (x2.x - x0.x) * eta,
+                              x0.y + (x1.y - x0.y) * xi + (x2.y - x0.y) * eta, u6);
+            }
+            const double dv = val - u6[0], dgx = gx - u6[1], dgy = gy - u6[2];
+            const double dxx = hxx - u6[3], dxy = hxy - u6[4], dyy = hyy - u6[5];
             s0 += dv * dv * w;
             s1 += (dgx * dgx + dgy * dgy) * w;
             s2 += (dxx * dxx + 2.0 * dxy * dxy + dyy * dyy) * w;
@@ -301,20 +361,25 @@ __global__ void __launch_bounds__(128) k_morley_mass(int64_t nrows, int64_t nt, 
 __global__ void k_morley_load_vector(int64_t nrows, int64_t nt, int nq, const double *__restrict__ XW,
                                      const double2 *__restrict__ pxy, const int32_t *__restrict__ t,
                                      const int64_t *__restrict__ r2e_ptr, const int32_t *__restrict__ r2e_idx,
-                                     const double *__restrict__ fq, double *__restrict__ out) {
+                                     const double *__restrict__ fq, int problem, double eps,
+                                     double *__restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
     double acc = 0.0;
     for (int64_t p = r2e_ptr[r]; p < r2e_ptr[r + 1]; ++p) {
         const int32_t code = r2e_idx[p];
         const int64_t e = code >> 3;
+        const double2 x0 = pxy[t[e]], x1 = pxy[t[nt + e]], x2 = pxy[t[2 * nt + e]];
         MorleyFrame F;
-        morley_frame(pxy[t[e]], pxy[t[nt + e]], pxy[t[2 * nt + e]], F);
+        morley_frame(x0, x1, x2, F);
         double s = 0.0;
         for (int q = 0; q < nq; ++q) {
             const double xi = XW[q], eta = XW[nq + q], w = XW[2 * nq + q] * 2.0 * F.area;
             const double lam[3] = {1.0 - xi - eta, xi, eta};
-            s += fq[e * nq + q] * morley_value(F, code & 7, lam) * w;
+            const double f = fq ? fq[e * nq + q]
+                                : problem_exact_value(problem, x0.x + (x1.x - x0.x) * xi + (x2.x - x0.x) * eta,
+                                                      x0.y + (x1.y - x0.y) * xi + (x2.y - x0.y) * eta);
+            s += f * morley_value(F, code & 7, lam) * w;
         }
         acc += s;
     }
@@ -354,7 +419,19 @@ extern "C" int mwx_load_vector(int64_t nrows, int64_t nt, int32_t ndpe, int32_t 
     if (nrows <= 0 || nt <= 0 || (ndpe != 3 && ndpe != 6) || nq <= 0 || !xw || !pxy || !t || !r2e_ptr || !r2e_idx || !fq || !out)
         return MWX_E_BADARG;
     k_load_vector<<<grid_for(nrows, 128), 128, 0, as_stream(stream)>>>(nrows, nt, ndpe, nq, xw, (const double2 *)pxy, t,
-                                                                     r2e_ptr, r2e_idx, fq, out);
+                                                                     r2e_ptr, r2e_idx, fq, 0, 0.0, out);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_load_vector_problem(int32_t problem, double eps, int64_t nrows, int64_t nt, int32_t ndpe, int32_t nq,
+                                       const double *xw, const double *pxy, const int32_t *t, const int64_t *r2e_ptr,
+                                       const int32_t *r2e_idx, double *out, void *stream) {
+    if ((problem != 1 && problem != 3) || nrows <= 0 || nt <= 0 || (ndpe != 3 && ndpe != 6) || nq <= 0 || !xw || !pxy || !t ||
+        !r2e_ptr || !r2e_idx || !out)
+        return MWX_E_BADARG;
+    k_load_vector<<<grid_for(nrows, 128), 128, 0, as_stream(stream)>>>(nrows, nt, ndpe, nq, xw, (const double2 *)pxy, t,
+                                                                     r2e_ptr, r2e_idx, nullptr, problem, eps, out);
     MWX_LAUNCH_CHECK();
     return 0;
 }
@@ -378,7 +455,22 @@ extern "C" int mwx_morley_error_sums(int64_t nt, int32_t nq, const double *xw, c
     const int64_t nb = (nt + 127) / 128;
     Scratch<double> partials(st);
     MWX_CUDA(partials.alloc((size_t)(3 * nb)));
-    k_morley_errors<<<(unsigned)nb, 128, 0, st>>>(nt, nq, xw, (const double2 *)pxy, t, edofs, uh, exact6, partials.p);
+    k_morley_errors<<<(unsigned)nb, 128, 0, st>>>(nt, nq, xw, (const double2 *)pxy, t, edofs, uh, exact6, 0, partials.p);
+    MWX_LAUNCH_CHECK();
+    k_fold3<<<1, 1024, 0, st>>>(nb, partials.p, sums3);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_morley_error_sums_problem(int32_t problem, int64_t nt, int32_t nq, const double *xw, const double *pxy,
+                                             const int32_t *t, const int32_t *edofs, const double *uh, double *sums3,
+                                             void *stream) {
+    if ((problem != 1 && problem != 3) || nt <= 0 || nq <= 0 || !xw || !pxy || !t || !edofs || !uh || !sums3) return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    const int64_t nb = (nt + 127) / 128;
+    Scratch<double> partials(st);
+    MWX_CUDA(partials.alloc((size_t)(3 * nb)));
+    k_morley_errors<<<(unsigned)nb, 128, 0, st>>>(nt, nq, xw, (const double2 *)pxy, t, edofs, uh, nullptr, problem, partials.p);
     MWX_LAUNCH_CHECK();
     k_fold3<<<1, 1024, 0, st>>>(nb, partials.p, sums3);
     MWX_LAUNCH_CHECK();
@@ -402,7 +494,7 @@ extern "C" int mwx_morley_load_vector(int64_t nrows, int64_t nt, int32_t nq, con
                                       const double *fq, double *out, void *stream) {
     if (nrows <= 0 || nt <= 0 || nq <= 0 || !xw || !pxy || !t || !r2e_ptr || !r2e_idx || !fq || !out) return MWX_E_BADARG;
     k_morley_load_vector<<<grid_for(nrows, 128), 128, 0, as_stream(stream)>>>(nrows, nt, nq, xw, (const double2 *)pxy, t,
-                                                                            r2e_ptr, r2e_idx, fq, out);
+                                                                            r2e_ptr, r2e_idx, fq, 0, 0.0, out);
     MWX_LAUNCH_CHECK();
     return 0;
 }

@@ -255,6 +255,12 @@ int mwx_assemble_lagrange_laplace(int64_t nrows, int64_t nt, int32_t ndpe, const
 int mwx_load_vector(int64_t nrows, int64_t nt, int32_t ndpe, int32_t nq, const double *xw, const double *pxy,
                     const int32_t *t, const int64_t *r2e_ptr, const int32_t *r2e_idx, const double *fq,
                     double *out, void *stream);
+/* Same, with the load of a NAMED problem evaluated on the device instead of host samples: problem 1 = 'ex1'
+ * (f = eps^2 lap^2 u - lap u, u = (sin pi x sin pi y)^2, ref main/example1/run.py:275-288), problem 3 = 'ex3'
+ * (f = 2 pi^2 sin pi x sin pi y, ref run.py:466-472).  For meshes where nt*nq host samples are not an option. */
+int mwx_load_vector_problem(int32_t problem, double eps, int64_t nrows, int64_t nt, int32_t ndpe, int32_t nq,
+                            const double *xw, const double *pxy, const int32_t *t, const int64_t *r2e_ptr,
+                            const int32_t *r2e_idx, double *out, void *stream);
 /* f2 = asm(wv_load, basis['w'], basis['u']) * wh, ref run.py:126-131,211, applied without storing the rectangular
  * matrix: out[r] = sum_K int grad(w_h) . grad(phi_r) over the Morley rows (r2e = Morley incidence). */
 int mwx_wv_action(int64_t nrows, int64_t nt, int32_t ndpe_w, const double *pxy, const int32_t *t,
@@ -265,6 +271,11 @@ int mwx_wv_action(int64_t nrows, int64_t nt, int32_t ndpe_w, const double *pxy, 
 int mwx_morley_error_sums(int64_t nt, int32_t nq, const double *xw, const double *pxy, const int32_t *t,
                           const int32_t *edofs, const double *uh, const double *exact6, double *sums3,
                           void *stream);
+/* Same against the exact solution of a named problem (1 = 'ex1', 3 = 'ex3'; ref run.py:290-309, 474-493) evaluated
+ * on the device at the quadrature points. */
+int mwx_morley_error_sums_problem(int32_t problem, int64_t nt, int32_t nq, const double *xw, const double *pxy,
+                                  const int32_t *t, const int32_t *edofs, const double *uh, double *sums3,
+                                  void *stream);
 
 /* project(exact_u, basis_to=basis['u']) of example 3 (ref main/example3/run.py:66, main/example3/utils.py:494-565):
  * Morley mass matrix (quadrature, same pattern as K2) and the load vector int f phi_r (f sampled at the points). */

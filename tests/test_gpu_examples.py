@@ -139,3 +139,24 @@ def test_project_is_the_l2_projection(cuda):
     assert abs(M - M_o).max() <= 1e-12 * abs(M_o).max()
     x = F.project(prob.u, ub)
     assert np.linalg.norm(x - x_o) <= 1e-10 * np.linalg.norm(x_o)
+
+
+@pytest.mark.parametrize('name,eps', [('ex1', 0.1), ('ex3', 1.0)])
+def test_device_problem_data_matches_host_samples(cuda, name, eps):
+    """problems.Problem: the load and the exact solution evaluated by the kernels (mwx_load_vector_problem,
+    mwx_morley_error_sums_problem) against the same Python functions sampled on the host."""
+    import fem_forth_perturb_b200 as F
+    gm = F.MeshTri().refine(4)
+    prob = F.Problem(name, eps)
+    uh = np.random.default_rng(5).standard_normal(gm.nv + gm.nf)
+    ub = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+    for elem in (F.ElementTriP1(), F.ElementTriP2()):
+        wb = F.InteriorBasis(gm, elem, intorder=5)
+        f_host = F.asm_gpu(prob.f_load, wb)
+        f_dev = F.asm_gpu(prob.f_load, wb, on_device=True).cpu().numpy()
+        assert np.max(np.abs(f_dev - f_host)) <= 1e-12 * np.max(np.abs(f_host))
+    host = F.morley_error_norms(ub, uh, prob.exact_u, prob.dexact_u, prob.ddexact)
+    dev = F.morley_error_norms(ub, uh, problem=prob)
+    assert np.allclose(dev, host, rtol=1e-12, atol=0)
+    with pytest.raises(NotImplementedError):
+        F.asm_gpu(F.LinearForm(lambda v, w: v), wb, on_device=True)
