@@ -177,8 +177,8 @@ def main():
                     help="skip the one untimed solve on the reference's Ruge-Stueben hierarchy that mode 'sa' reports beside itself")
     ap.add_argument('--no-ex1', action='store_true', help='skip the real example-1 problem (error norms vs the exact solution)')
     ap.add_argument('--no-same-config', action='store_true', help="skip the level-8 pass in the reference's own mode")
-    ap.add_argument('--tight-tol', type=float, default=1e-10,
-                    help='second tolerance of the ex1 check: where both hierarchies have converged, their solutions must agree')
+    ap.add_argument('--ex1-rs-top', action='store_true',
+                    help="also run the reference's RS hierarchy on the real ex1 right-hand side at the top level (thousands of iterations)")
     ap.add_argument('--asm-levels', type=int, nargs='*', default=[11, 13],
                     help='extra levels of the assembly-only microbench reported in the line (the main level is timed in the step)')
     ap.add_argument('--microbench', action='store_true',
@@ -253,19 +253,54 @@ def ex1_pipeline(torch, F, gm, ubasis, plan, K2, eps, solve_u, w_mode, tol):
     I_dev = torch.from_numpy(np.ascontiguousarray(plan.I, dtype=np.int64)).to(gm.device)
     out = {'w_solve': {'iters': its_w, 'info': info_w, 'mode': w_mode, 'n': K1c.shape[0], 'amg_setup_s': t_wsetup}}
     sols = {}
+    bn = float(torch.linalg.norm(bc))
     for name, fn in solve_u.items():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        x, its, info = fn(Kc, bc)
+        x, its, info, first_hit = fn(Kc, bc)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         uh = torch.zeros(ubasis.N, dtype=torch.float64, device=gm.device)
         uh[I_dev] = x
         L2, D1, D2 = F.morley_error_norms(ubasis, uh, problem=prob)
-        out[name] = {'iters': its, 'info': info, 's_per_solve': dt, 'L2': L2, 'H1': L2 + D1, 'H2': L2 + D1 + D2,
-                     'energy': float(np.sqrt(eps ** 2 * D2 ** 2 + D1 ** 2))}
+        out[name] = {'iters': its, 'info': info, 'first_iter_with_recurrence_residual_below_tol': first_hit,
+                     'true_rel_residual': float(torch.linalg.norm(bc - Kc.dot(x))) / bn, 's_per_solve': dt,
+                     'L2': L2, 'H1': L2 + D1, 'H2': L2 + D1 + D2, 'energy': float(np.sqrt(eps ** 2 * D2 ** 2 + D1 ** 2))}
         sols[name] = x
     return out, sols
+
+
+def ex1_level(torch, F, level, eps, tol, modes, maxiter, setup=None):
+    """ex1 on one level with every hierarchy in `modes`; setup = (gm, basis, plan, K2, {mode: hierarchy}) to reuse the
+    bench's own objects.  Stops after 2 failed true-residual re-checks (mwx_pcg_amg_monitored): on the finest levels
+    tol * ||b|| lies below the fp64 floor eps_mach ||A|| ||x|| of the residual and scipy's rule can never be met."""
+    if setup is None:
+        gm = F.MeshTri().refine(level)
+        ub = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+        bf = gm.boundary_facets()
+        D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+        K2 = F.asm_gpu(eps ** 2 * F.a_load + F.b_load, ub)
+        plan = F.CondensePlan(K2, D=D)
+        Kc, _ = plan.apply(K2)
+        mls = {mode: F.AMGHierarchy(Kc, mode=mode) for mode in modes}
+        del Kc
+    else:
+        gm, ub, plan, K2, mls = setup
+
+    def solver(mode):
+        def fn(Kc_, bc_):
+            mon = {}
+            x, its, info, _ = F.pcg(Kc_, bc_, tol, maxiter[mode], amg=mls[mode], max_rechecks=2, monitor=mon)
+            return x, its, info, mon.get('first_hit')
+        return fn
+    res, sols = ex1_pipeline(torch, F, gm, ub, plan, K2, eps, {m: solver(m) for m in modes if m in mls},
+                             modes[0] if modes[0] in ('sa', 'chebyshev') else 'chebyshev', tol)
+    res['dofs'] = ub.N
+    names = [m for m in modes if m in sols]
+    if len(names) == 2:
+        a, b2 = sols[names[0]], sols[names[1]]
+        res[f'rel_l2_diff_{names[0]}_vs_{names[1]}'] = float(torch.linalg.norm(a - b2) / torch.linalg.norm(b2))
+    return res
 
 
 def same_config_level8(torch, F, L, level, tol):
@@ -323,6 +358,10 @@ def run_single(args, torch, F, L, dev, local):
     torch.cuda.synchronize()
     t_pattern = time.perf_counter() - t0
     N, nt, nnz = basis.N, gm.nt, pat['nnz']
+    t0 = time.perf_counter()
+    asm_kernel = F.assembly_kernel_name(basis)     # builds the tile plan of the element-once kernel (setup)
+    torch.cuda.synchronize()
+    t_tileplan = time.perf_counter() - t0
     # Dirichlet set of easy_boundary (ref main/example1/run.py:86-104): boundary vertices + boundary facets
     bf = gm.boundary_facets()
     D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
@@ -451,34 +490,21 @@ def run_single(args, torch, F, L, dev, local):
         by_mode['rel_diff_between_modes_tol1e-8_manufactured_rhs'] = float(torch.linalg.norm(xa - xb) / torch.linalg.norm(xb))
     del x_by_mode
 
-    # ---------------------------------------------------------------- the real example-1 problem at this level (and one below)
+    # ---------------------------------------------------------------- the real example-1 problem on this level and the two below
     ex1 = None
+    ex1_maxiter = {m: (200 if m == 'sa' else 3000) for m in modes}
     if not args.no_ex1:
         ex1 = {'what': "ref main/example1/run.py solve_problem1 (w in P1, eps = %g, tol = %g) on the device; errors vs the exact "
                        "solution u = (sin pi x sin pi y)^2; H1 = L2 + |.|_1h, H2 = H1 + |.|_2h, energy = sqrt(eps^2 |.|_2h^2 + |.|_1h^2) "
-                       "as the reference prints them (run.py:519-543)" % (EPS, TOL), 'levels': {}}
+                       "as the reference prints them (run.py:519-543).  A solve stops on scipy's rule or after 2 failed true-residual "
+                       "re-checks (fp64 floor of the residual, see true_rel_residual); the reference's RS hierarchy is only run "
+                       "where its iteration count stays bounded (levels below the top one)" % (EPS, TOL), 'levels': {}}
         try:
-            def solver(mode, tol, ml_by_mode):
-                def fn(Kc_, bc_):
-                    x, its, info, _ = F.pcg(Kc_, bc_, tol, 600, amg=ml_by_mode[mode])
-                    return x, its, info
-                return fn
-            tight = args.tight_tol
-            solve_u = {}
-            for mode in modes:
-                solve_u[f'{mode}_tol{TOL:g}'] = solver(mode, TOL, mls)
-            for mode in modes:
-                solve_u[f'{mode}_tol{tight:g}'] = solver(mode, tight, mls)
-            res, sols = ex1_pipeline(torch, F, gm, basis, plan, K2, EPS, solve_u, args.mode if args.mode in ('sa', 'chebyshev') else 'chebyshev', TOL)
-            if len(modes) == 2:
-                for tol in (TOL, tight):
-                    a, b2 = sols[f'{modes[0]}_tol{tol:g}'], sols[f'{modes[1]}_tol{tol:g}']
-                    res[f'rel_l2_diff_{modes[0]}_vs_{modes[1]}_tol{tol:g}'] = float(torch.linalg.norm(a - b2) / torch.linalg.norm(b2))
-            ex1['levels'][str(args.level)] = res
-            del sols
+            top_modes = [m for m in modes if m == 'sa' or args.ex1_rs_top] or modes[:1]
+            ex1['levels'][str(args.level)] = ex1_level(torch, F, args.level, EPS, TOL, top_modes, ex1_maxiter,
+                                                       setup=(gm, basis, plan, K2, mls))
         except Exception as exc:
             ex1['levels'][str(args.level)] = {'error': repr(exc)[:300]}
-        solve_u = solver = None                      # the closures hold the hierarchies
 
     # free the big level before the side measurements
     same_cfg = None
@@ -518,28 +544,21 @@ def run_single(args, torch, F, L, dev, local):
     for r in rs:
         r.pop('x', None)
     torch.cuda.empty_cache()
-    if ex1 is not None and args.level >= 9:
-        lvl = args.level - 1
-        try:
-            gm1 = F.MeshTri().refine(lvl)
-            ub1 = F.InteriorBasis(gm1, F.ElementTriMorley(), intorder=5)
-            bf1 = gm1.boundary_facets()
-            D1 = np.concatenate((np.unique(gm1.facets[:, bf1]), bf1 + gm1.nv))
-            K21 = F.asm_gpu(form, ub1)
-            plan1 = F.CondensePlan(K21, D=D1)
-            Kc1, _ = plan1.apply(K21)
-            mls1 = {mode: F.AMGHierarchy(Kc1, mode=mode) for mode in modes}
-            solve_u = {f'{mode}_tol{TOL:g}': (lambda Kc_, bc_, mode=mode: F.pcg(Kc_, bc_, TOL, 600, amg=mls1[mode])[:3]) for mode in modes}
-            res, sols = ex1_pipeline(torch, F, gm1, ub1, plan1, K21, EPS, solve_u, args.mode if args.mode in ('sa', 'chebyshev') else 'chebyshev', TOL)
-            ex1['levels'][str(lvl)] = res
-            hi = ex1['levels'].get(str(args.level), {})
-            for name in solve_u:                        # convergence orders level L-1 -> L (reference table: ~2 / 2 / 1 / 2 ... )
-                if name in hi and name in res:
-                    hi[name]['orders_vs_level_below'] = {k: float(-np.log2(hi[name][k] / res[name][k])) for k in ('L2', 'H1', 'H2', 'energy')}
-            del sols, mls1, Kc1, plan1, K21, ub1, gm1
-        except Exception as exc:
-            ex1['levels'][str(lvl)] = {'error': repr(exc)[:300]}
-        torch.cuda.empty_cache()
+    if ex1 is not None:
+        for lvl in (args.level - 1, args.level - 2):
+            if lvl < 3:
+                continue
+            try:
+                ex1['levels'][str(lvl)] = ex1_level(torch, F, lvl, EPS, TOL, modes, ex1_maxiter)
+            except Exception as exc:
+                ex1['levels'][str(lvl)] = {'error': repr(exc)[:300]}
+            torch.cuda.empty_cache()
+        for lvl in (args.level, args.level - 1):         # convergence orders between consecutive levels (reference table: 2 / 2 / 1 / 1..2)
+            hi, lo = ex1['levels'].get(str(lvl), {}), ex1['levels'].get(str(lvl - 1), {})
+            for name in modes:
+                if isinstance(hi.get(name), dict) and isinstance(lo.get(name), dict):
+                    hi[name]['orders_vs_level_below'] = {k: float(-np.log2(hi[name][k] / lo[name][k]))
+                                                         for k in ('L2', 'H1', 'H2', 'energy')}
     if not args.no_same_config:
         try:
             same_cfg = {'gpu': same_config_level8(torch, F, L, args.ref_level, TOL)}
@@ -581,13 +600,13 @@ def run_single(args, torch, F, L, dev, local):
                  'skfem_numbering_ms': mean('spmv_skfem', rs),
                  'skfem_numbering_gbs': spmv_bytes / (mean('spmv_skfem', rs) * 1e-3) / 1e9},
         'reorder_ms': mean('reorder', rs),
-        'setup_s': {'mesh_refine': t_mesh, 'pattern_slotmap': t_pattern, 'condense_plan': t_cplan,
+        'setup_s': {'mesh_refine': t_mesh, 'pattern_slotmap': t_pattern, 'assembly_tile_plan': t_tileplan, 'condense_plan': t_cplan,
                     'amg_total': t_amg[args.mode], 'amg_total_by_mode': t_amg},
         'roofline': {'kernel': 'k_spmv (CSR SpMV, fine level, solver numbering)', 'bound': 'hbm', 'achieved': spmv_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': spmv_gbs / peak,
                      'traffic': kernel_traffic('k_spmv', level_main), 'peak_source': peak_src,
                      'algorithmic_bytes': spmv_bytes},
-        'roofline_assembly': {'kernel': F.assembly_kernel_name(), 'bound': 'hbm', 'achieved': asm_gbs,
+        'roofline_assembly': {'kernel': asm_kernel, 'bound': 'hbm', 'achieved': asm_gbs,
                               'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                               'traffic': kernel_traffic('assembly', level_main),
                               'algorithmic_bytes': asm_bytes,

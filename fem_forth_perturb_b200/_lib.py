@@ -41,6 +41,10 @@ _SIGNATURES = {
     'mwx_assemble_morley': [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, i32, vp, vp],
     'mwx_assemble_penalty': [i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp, vp],
     'mwx_assemble_morley_rows': [i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, vp, vp],
+    'mwx_asm_plan_create': [i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, ctypes.POINTER(vp), vp],
+    'mwx_asm_plan_destroy': [vp],
+    'mwx_asm_plan_info': [vp, vp],
+    'mwx_assemble_morley_plan': [vp, vp, f64, f64, i32, vp, vp],
     'mwx_axpby': [i64, f64, vp, f64, vp, vp, vp],
     'mwx_dist_rows_count': [i64, vp, vp, vp, vp, vp, vp, vp],
     'mwx_dist_rows_fill': [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
@@ -84,9 +88,10 @@ _SIGNATURES = {
     'mwx_amg_set_chebyshev': [vp, i32, f64],
     'mwx_amg_destroy_dev': [vp],
     'mwx_amg_vcycle': [vp, vp, vp, vp],
+    'mwx_pcg_amg_monitored': [vp, i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, _pi64, vp],
     'mwx_pcg_amg': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp],
 }
-_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev'}
+_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev', 'mwx_asm_plan_destroy'}
 
 ERRORS = {-1: 'MWX_E_BADARG', -2: 'MWX_E_CAPACITY', -3: 'MWX_E_NOCONV', -4: 'MWX_E_NOMEM'}
 

@@ -214,7 +214,7 @@ def asm_load(form, basis, on_device=False):
     return out.cpu().numpy()
 
 
-def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False, on_device=False):
+def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False, on_device=False, kernel=None):
     """Assemble ``form`` on ``ubasis`` -> :class:`DeviceCSR` (``.tocsr()`` gives scipy's matrix).
 
     ``form``: a descriptor from :mod:`forms` (or a linear combination such as
@@ -223,6 +223,8 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False, on
     Facet forms are returned on the INTERIOR pattern so that ``eps**2*A + eps**2*P + B`` is a device axpby.
     ``out`` / ``accumulate``: write the values into an existing nnz-sized device vector, or add to it (Morley
     interior forms; the penalty forms always add into ``out``).
+    ``kernel``: None = the tiled element-once kernel when the mesh fits its plan, else the row-gather kernel;
+    'tiles' / 'rows' force one of them (A/B comparisons, tests).
     """
     torch = L.require_cuda()
     from .forms import LinearFormGPU
@@ -288,6 +290,13 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False, on
     m = ubasis.mesh
     pat = ubasis.pattern()
     vals = out if out is not None else torch.empty(pat['nnz'], dtype=torch.float64, device=m.device)
+    tp = _tile_plan(ubasis) if kernel != 'rows' else None
+    if kernel == 'tiles' and tp is None:
+        raise L.MwxError("asm_gpu(kernel='tiles'): this mesh does not fit the tile plan (see mwx_asm_plan_create)")
+    if tp is not None:
+        tp.assemble(m, f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0), vals, accumulate and out is not None)
+        return DeviceCSR(pat['indptr'], pat['indices'], vals, (ubasis.N, ubasis.N), pat['key'], coords=ubasis.dof_coords,
+                         candidates=ubasis.nullspace_candidates)
     L.check(lib.mwx_assemble_morley(ubasis.N, m.nt, L.ptr(m.d_pxy), L.ptr(m.d_t), L.ptr(pat['exy']), 1,
                                     L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']), L.ptr(pat['slot8']),
                                     L.ptr(pat['indptr']), f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0),
@@ -300,9 +309,83 @@ def asm_gpu(form, ubasis, vbasis=None, sigma=5.0, out=None, accumulate=False, on
 asm = asm_gpu
 
 
-def assembly_kernel_name():
-    """Name of the kernel(s) behind ``asm_gpu(eps**2 * a_load + b_load, basis)`` in this build (bench.py's roofline label)."""
-    return 'k_element_geometry + k_assemble_morley_persistent'
+class TilePlan:
+    """Plan of the tiled Morley kernel (``mwx_asm_plan_create``) for one destination layout; owns the device blobs.
+
+    rows: device int32 skfem DOF per destination row in locality order; dst_off / dst_len / dst_col: where each row
+    lives in the destination value array and which skfem DOF each of its entries is."""
+
+    def __init__(self, basis, rows, dst_off, dst_len, dst_col):
+        m, pat = basis.mesh, basis.pattern()
+        self._h = ctypes.c_void_p()
+        self._keep = (rows, dst_off, dst_len, dst_col)
+        rc = L.lib().mwx_asm_plan_create(rows.numel(), L.ptr(rows), L.ptr(dst_off), L.ptr(dst_len), L.ptr(dst_col), m.nt,
+                                         L.ptr(m.d_t), L.ptr(basis.d_element_dofs), L.ptr(pat['r2e_ptr']),
+                                         L.ptr(pat['r2e_idx']), ctypes.byref(self._h), L.stream())
+        self.ok = rc == 0
+        if rc not in (0, -2):                       # -2 = MWX_E_CAPACITY: the mesh needs the row-gather kernel
+            L.check(rc, 'mwx_asm_plan_create')
+        self._keep = None                           # the plan holds its own copies of everything it needs
+        self.info = None
+        if self.ok:
+            info = np.zeros(4, dtype=np.int64)
+            L.check(L.lib().mwx_asm_plan_info(self._h, L.ptr(info)), 'mwx_asm_plan_info')
+            self.info = dict(tiles=int(info[0]), rows_per_tile=int(info[1]), entry_bytes=int(info[2]), geometry_bytes=int(info[3]))
+
+    @classmethod
+    def for_matrix(cls, basis):
+        """Plan for the global K2 of ``basis`` (skfem CSR layout): rows in Hilbert order of the DOF locations."""
+        torch = L.require_cuda()
+        pat = basis.pattern()
+        order = hilbert_order(basis.dof_coords())
+        indptr = pat['indptr']
+        rows = order.to(torch.int32)
+        dst_off = indptr[order].contiguous()
+        dst_len = (indptr[1:] - indptr[:-1])[order].to(torch.int32).contiguous()
+        return cls(basis, rows, dst_off, dst_len, pat['indices'])
+
+    def assemble(self, mesh, ca, cb, values, accumulate=False):
+        L.check(L.lib().mwx_assemble_morley_plan(self._h, L.ptr(mesh.d_pxy), float(ca), float(cb), 1 if accumulate else 0,
+                                                 L.ptr(values), L.stream()), 'mwx_assemble_morley_plan')
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                L.lib().mwx_asm_plan_destroy(self._h)
+        except Exception:
+            pass
+
+
+def hilbert_order(coords):
+    """argsort of the Hilbert-curve keys of (n, 2) device points (new -> old), int64."""
+    torch = L.require_cuda()
+    xy = coords.contiguous()
+    n = xy.shape[0]
+    lo, hi = xy.min(dim=0).values, xy.max(dim=0).values
+    extent = float((hi - lo).max().item()) or 1.0
+    keys = torch.empty(n, dtype=torch.int64, device=xy.device)
+    L.check(L.lib().mwx_hilbert_keys(n, L.ptr(xy), float(lo[0].item()), float(lo[1].item()), extent, L.ptr(keys), L.stream()),
+            'mwx_hilbert_keys')
+    return torch.sort(keys, stable=True).indices               # library sort: setup only
+
+
+def _tile_plan(basis):
+    """The cached tile plan of a Morley basis, or None when the row-gather kernel has to be used."""
+    import os
+    if os.environ.get('MWX_ASM_KERNEL', 'tiles') != 'tiles':
+        return None
+    pat = basis.pattern()
+    if 'tile_plan' not in pat:
+        plan = TilePlan.for_matrix(basis)
+        pat['tile_plan'] = plan if plan.ok else None
+    return pat['tile_plan']
+
+
+def assembly_kernel_name(basis=None):
+    """Name of the kernel(s) behind ``asm_gpu(eps**2 * a_load + b_load, basis)`` (bench.py's roofline label)."""
+    if basis is None or _tile_plan(basis) is not None:
+        return 'k_assemble_morley_tiles (tiled, every element once; plan built at setup)'
+    return 'k_element_geometry + k_assemble_morley_persistent (row-gather fallback)'
 
 
 def morley_error_norms(basis, uh, exact_u=None, dexact_u=None, ddexact=None, problem=None):

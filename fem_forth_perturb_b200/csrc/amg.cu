@@ -456,6 +456,19 @@ extern "C" int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, c
                     iters_host, info_host, resid_host, as_stream(stream));
 }
 
+extern "C" int mwx_pcg_amg_monitored(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_t *indices,
+                                     const double *values, const double *b, double *x, double tol, int64_t maxiter,
+                                     int32_t max_rechecks, double *work, int64_t *iters_host, int32_t *info_host,
+                                     double *resid_host, int64_t *first_hit_host, void *stream) {
+    if (!d || n <= 0 || !indptr || !indices || !values || !b || !x || !work || !iters_host || !info_host || !resid_host ||
+        max_rechecks < 0)
+        return MWX_E_BADARG;
+    if (d->lv[0].A.rows != n) return MWX_E_BADARG;
+    double *r = work, *z = work + n, *p = work + 2 * n, *q = work + 3 * n;
+    return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, nullptr, amg_precond, d, r, z, p, q,
+                    iters_host, info_host, resid_host, as_stream(stream), max_rechecks, first_hit_host);
+}
+
 extern "C" int mwx_smoother_first(int64_t n, const double *b, const double *dinv, double c2, double *x, double *d,
                                   void *stream) {
     if (n <= 0 || !b || !dinv || !x || !d) return MWX_E_BADARG;

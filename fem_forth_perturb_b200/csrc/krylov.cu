@@ -480,8 +480,11 @@ int launch_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices
 int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
              const double *b, double *x, double tol, int64_t maxiter, const double *dinv,
              PrecondFn precond, void *ctx, double *r, double *z, double *p, double *q,
-             int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st) {
+             int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st, int max_rechecks,
+             int64_t *first_hit_host) {
     Scratch<CgScalars> sc(st);
+    int rechecks = 0;
+    if (first_hit_host) *first_hit_host = 0;
     Scratch<double> partials(st);
     MWX_CUDA(sc.alloc(1));
     MWX_CUDA(partials.alloc(2 * RED_MAX_BLOCKS));
@@ -531,6 +534,7 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
         *iters_host = it; *resid_host = rn;
         if (!(rn == rn)) { *info_host = (int32_t)(it < 0x7fffffff ? it : 0x7fffffff); return MWX_E_NOCONV; }
         if (rn <= atol) {
+            if (first_hit_host && *first_hit_host == 0) *first_hit_host = it;
             if (it == 1) return 0;
             // true-residual re-check; on failure CG continues from the recomputed r
             rc = launch_residual(n, indptr, indices, values, x, b, r, jacobi ? dinv : nullptr, sc.p, partials.p, st);
@@ -543,6 +547,13 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
             rn = sqrt(h[0]);
             *resid_host = rn;
             if (rn <= atol) return 0;
+            // scipy 1.4.1 carries on from the recomputed residual until maxiter.  max_rechecks > 0 (an extension, off
+            // by default): give up after that many failed re-checks - the recurrence has converged but the TRUE
+            // residual sits on its fp64 floor (eps_mach ||A|| ||x|| > tol ||b|| on very fine meshes).
+            if (max_rechecks > 0 && ++rechecks >= max_rechecks) {
+                *info_host = (int32_t)(it < 0x7fffffff ? it : 0x7fffffff);
+                return 0;
+            }
         }
     }
     *info_host = (int32_t)(maxiter < 0x7fffffff ? maxiter : 0x7fffffff);
@@ -603,7 +614,7 @@ extern "C" int mwx_pcg_jacobi(int64_t n, const int64_t *indptr, const int32_t *i
         MWX_LAUNCH_CHECK();
     }
     return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, precondition ? dinv : nullptr,
-                    nullptr, nullptr, r, nullptr, p, q, iters_host, info_host, resid_host, st);
+                    nullptr, nullptr, r, nullptr, p, q, iters_host, info_host, resid_host, st, 0, nullptr);
 }
 
 // ------------------------------------------------------------------ building blocks for the partitioned CG

@@ -55,6 +55,7 @@ typedef int (*PrecondFn)(void *ctx, const double *r, double *z, cudaStream_t st)
 int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
              const double *b, double *x, double tol, int64_t maxiter, const double *dinv,
              PrecondFn precond, void *ctx, double *r, double *z, double *p, double *q,
-             int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st);
+             int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st, int max_rechecks = 0,
+             int64_t *first_hit_host = nullptr);
 
 }  // namespace mwx

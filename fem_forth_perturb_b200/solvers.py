@@ -282,7 +282,7 @@ class AMGHierarchy:
             pass
 
 
-def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=None):
+def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=None, max_rechecks=0, monitor=None):
     """Device PCG with scipy-1.4.1 semantics on a DeviceCSR / scipy matrix.  ``amg`` = a prebuilt
     :class:`AMGHierarchy` (hierarchy reuse across solves: north_star's "built once as timed setup"), else Jacobi /
     plain CG.  ``b`` numpy or device tensor.  Returns (x as a device tensor, iters, info, resid)."""
@@ -303,6 +303,15 @@ def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=No
         rc = L.lib().mwx_pcg_jacobi(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd), L.ptr(x),
                                     float(tol), mi, 1 if precondition else 0, L.ptr(work), ctypes.byref(iters),
                                     ctypes.byref(info), ctypes.byref(resid), L.stream())
+    elif max_rechecks or monitor is not None:
+        # diagnostics beyond scipy's cg (see mwx_pcg_amg_monitored): first iteration that met the tolerance on the
+        # recurrence residual, optional stop after `max_rechecks` failed true-residual re-checks
+        first = ctypes.c_int64(0)
+        rc = L.lib().mwx_pcg_amg_monitored(amg._dev, n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd),
+                                           L.ptr(x), float(tol), mi, int(max_rechecks), L.ptr(work), ctypes.byref(iters),
+                                           ctypes.byref(info), ctypes.byref(resid), ctypes.byref(first), L.stream())
+        if monitor is not None:
+            monitor['first_hit'] = int(first.value)
     else:
         rc = L.lib().mwx_pcg_amg(amg._dev, n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd),
                                  L.ptr(x), float(tol), mi, L.ptr(work), ctypes.byref(iters), ctypes.byref(info),

@@ -121,6 +121,33 @@ int mwx_assemble_morley_rows(int64_t nrows, const int32_t *row_ids, const int64_
                              const int64_t *r2e_ptr, const int32_t *r2e_idx, const uint8_t *slot8,
                              const int64_t *indptr, double ca, double cb, double *values, void *stream);
 
+/* ------------------------------------------------------------------ Morley element kernel, tiled form (the default)
+ * Same matrix as mwx_assemble_morley, organised by a PLAN built once per (mesh, destination layout):
+ *   row_dof[i]  (nrows)  skfem DOF of the i-th destination row, in a LOCALITY order (Hilbert curve over the DOF
+ *                        locations); the rows are cut into tiles of <= 256 consecutive entries of this list;
+ *   dst_off[i], dst_len[i]  where row i lives in the destination value array and how many entries it has;
+ *   dst_col[dst_off[i] + k] skfem DOF of the k-th destination entry of row i (any order; columns of the element
+ *                        matrices that do not occur are dropped - a condensed or rank-local layout).
+ * For the global K2: row_dof = Hilbert order of all DOFs, dst_off = indptr[row_dof], dst_col = indices.
+ * t (3*nt), edofs (6*nt), r2e_* as for mwx_pattern_*.  Per tile the plan stores the unique vertices / elements of
+ * the patch and, per destination entry, the <= 2 contributing (element, local pair) codes; the kernel evaluates
+ * every unique element of a tile ONCE (21 entries of the symmetric local matrix, shared memory) and writes each
+ * value with one coalesced store - no atomics, fixed summation order (ascending element id).
+ * Returns MWX_E_CAPACITY when the mesh does not fit the tile limits (vertex valence > 16, rows longer than 64
+ * entries, an edge with three triangles): callers then use mwx_assemble_morley. */
+typedef struct mwx_asm_plan mwx_asm_plan_t;
+int mwx_asm_plan_create(int64_t nrows, const int32_t *row_dof, const int64_t *dst_off, const int32_t *dst_len,
+                        const int32_t *dst_col, int64_t nt, const int32_t *t, const int32_t *edofs,
+                        const int64_t *r2e_ptr, const int32_t *r2e_idx, mwx_asm_plan_t **out, void *stream);
+void mwx_asm_plan_destroy(mwx_asm_plan_t *plan);
+/* info4 = {tiles, rows per tile, bytes of the entry blobs, bytes of the geometry blobs}. */
+int mwx_asm_plan_info(const mwx_asm_plan_t *plan, int64_t *info4);
+/* values[dst] = ca * (hess u : hess v) + cb * (grad u . grad v) for every destination entry of the plan
+ * (ref main/example1/run.py:110-123, 210); pxy = CURRENT vertex coordinates (interleaved x, y; skfem vertex order).
+ * accumulate != 0 adds into values. */
+int mwx_assemble_morley_plan(const mwx_asm_plan_t *plan, const double *pxy, double ca, double cb,
+                             int32_t accumulate, double *values, void *stream);
+
 /* ------------------------------------------------------------------ condense (glue A -> B)
  * Replaces condense(K2, f2, D=...) ref main/example1/utils.py:384-460:
  *   Aout = A[I].T[I].T,  bout = b[I] - A[I].T[D].T @ x[D].
@@ -244,6 +271,15 @@ int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_
                 const double *values, const double *b, double *x, double tol, int64_t maxiter,
                 double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
                 void *stream);
+
+/* Same solve with two diagnostics that scipy's cg does not have (both off = mwx_pcg_amg): *first_hit_host = the first
+ * iteration whose recurrence residual met the tolerance; max_rechecks > 0 stops after that many FAILED true-residual
+ * re-checks (info = iteration count, *resid_host = the true residual) instead of iterating to maxiter - on very fine
+ * meshes eps_mach ||A|| ||x|| exceeds tol ||b|| and the scipy 1.4.1 rule can never be met in fp64. */
+int mwx_pcg_amg_monitored(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_t *indices,
+                          const double *values, const double *b, double *x, double tol, int64_t maxiter,
+                          int32_t max_rechecks, double *work, int64_t *iters_host, int32_t *info_host,
+                          double *resid_host, int64_t *first_hit_host, void *stream);
 
 /* ------------------------------------------------------------------ callers either side of the hot path
  * K1 = asm(laplace, basis['w']) for P1 (ndpe 3) / P2 (ndpe 6), ref main/example1/run.py:149-154,198 (closed form). */

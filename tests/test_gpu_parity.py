@@ -145,6 +145,73 @@ def test_assembly_accumulate_and_repeatability(cuda):
     assert _relmax(Kacc.tocsr(), K1.tocsr()) < 1e-14
 
 
+def _fan_mesh(valence, seed=3):
+    rng = np.random.default_rng(seed)
+    ang = np.sort(rng.uniform(0, 2 * np.pi, valence))
+    p = np.hstack((np.zeros((2, 1)), np.vstack((np.cos(ang), np.sin(ang)))))
+    t = np.array([[0, 1 + k, 1 + (k + 1) % valence] for k in range(valence)]).T
+    return p, t
+
+
+@pytest.mark.parametrize('case', ['square3', 'square7', 'lshape5', 'fan7', 'perturbed'])
+def test_tiled_kernel_equals_row_kernel_and_oracle(cuda, case):
+    """The default (tiled, every element once) kernel against the row-gather kernel of round 1 and the oracle:
+    same CSR, values to round-off, bit-identical run to run, accumulate path, partial tiles, irregular valence."""
+    import fem_forth_perturb_b200 as F
+    if case.startswith('square'):
+        lvl = int(case[-1])
+        om, gm = _meshes(lvl)
+    elif case == 'lshape5':
+        om, gm = _meshes(5, lshaped=True)
+    elif case == 'fan7':
+        p, t = _fan_mesh(7)
+        om, gm = OMesh(p, t).refine(3), F.MeshTri(p, t).refine(3)
+    else:
+        om0 = OMesh().refine(5)
+        rng = np.random.default_rng(11)
+        inner = np.setdiff1d(np.arange(om0.nv), om0.boundary_nodes())
+        p = om0.p.copy()
+        p[:, inner] += 0.004 * rng.standard_normal((2, len(inner)))
+        om, gm = OMesh(p, om0.t), F.MeshTri(p, om0.t)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+    form = 0.04 * F.a_load + F.b_load
+    Kt = F.asm_gpu(form, basis, kernel='tiles')
+    Kr = F.asm_gpu(form, basis, kernel='rows')
+    assert F.assembly_kernel_name(basis).startswith('k_assemble_morley_tiles')
+    info = basis.pattern()['tile_plan'].info
+    assert info['tiles'] == -(-basis.N // info['rows_per_tile']) and info['rows_per_tile'] in (16, 32, 64, 128, 256)
+    scale = float(Kr.d_data.abs().max())
+    assert float((Kt.d_data - Kr.d_data).abs().max()) <= 2e-14 * scale
+    Kt2 = F.asm_gpu(form, basis, kernel='tiles')
+    assert bool((Kt.d_data == Kt2.d_data).all())                   # fixed summation order: identical bits
+    Ksym = Kt.tocsr()
+    assert abs(Ksym - Ksym.T).max() == 0.0                         # one stored value per symmetric pair of the local matrix
+    Kacc = F.asm_gpu(0.04 * F.a_load, basis, kernel='tiles')
+    F.asm_gpu(F.b_load, basis, out=Kacc.d_data, accumulate=True, kernel='tiles')
+    assert float((Kacc.d_data - Kt.d_data).abs().max()) <= 2e-14 * scale
+    if case != 'square7':
+        K_or = pl.assemble_K2(OInterior(om, 'Morley', 5, shift=True), 0.2)
+        K = Kt.tocsr()
+        assert np.array_equal(K.indptr, K_or.indptr) and np.array_equal(K.indices, K_or.indices)
+        assert _relmax(K, K_or) < 1e-12
+
+
+def test_tile_plan_falls_back_on_high_valence(cuda):
+    """A vertex shared by 20 triangles exceeds the plan's limits (16 elements / 64 entries per row): asm_gpu then uses
+    the row-gather kernel - same matrix, no error."""
+    import fem_forth_perturb_b200 as F
+    p, t = _fan_mesh(20)
+    om, gm = OMesh(p, t), F.MeshTri(p, t)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley(), intorder=5)
+    K = F.asm_gpu(0.3 * F.a_load + F.b_load, basis)
+    assert basis.pattern()['tile_plan'] is None
+    assert F.assembly_kernel_name(basis).startswith('k_element_geometry')
+    with pytest.raises(F.MwxError):
+        F.asm_gpu(F.a_load, basis, kernel='tiles')
+    K_or = pl.assemble_K2(OInterior(om, 'Morley', 5, shift=True), np.sqrt(0.3))
+    assert np.array_equal(K.tocsr().indices, K_or.indices) and _relmax(K.tocsr(), K_or) < 1e-12
+
+
 def test_generic_triangles_lshape(cuda):
     """Non-right, differently oriented triangles: perturbed L-shape mesh."""
     import fem_forth_perturb_b200 as F
