@@ -46,8 +46,15 @@ constexpr int AT_DCAP = 1024;     // (row, element) pairs per tile (uniform mesh
 constexpr int AT_MAXP = 16;       // elements per row (vertex valence)
 constexpr int AT_MAXLEN = 64;     // destination entries per row
 constexpr int AT_MAXRUNS = 16;    // runs of equal row length inside a tile
-constexpr unsigned AT_NONE = 0xFFFFu, AT_DIAG = 0xFFFEu;
 constexpr int AT_NSYM = 21;       // upper triangle of the symmetric 6x6 local matrix
+constexpr int AT_LSTRIDE = AT_ECAP + 1;   // ODD stride (in doubles) of the local-matrix table loc[k * AT_LSTRIDE + e]: the lanes
+                                          // of a row read different k of the same one or two elements - with an even stride
+                                          // they all hit one bank (measured: 12 wavefronts per LDS.64 instead of 2)
+// The table has two more regions so that phase 2 is branch-free (value = loc[first] + loc[second], always):
+constexpr int AT_DIAG_BASE = AT_NSYM * AT_LSTRIDE;        // loc[AT_DIAG_BASE + row]: the row's diagonal (phase D)
+constexpr int AT_ZERO = AT_DIAG_BASE + AT_THREADS;        // loc[AT_ZERO] = 0.0: the "no second contribution" slot
+constexpr int AT_LOC_DOUBLES = AT_ZERO + 1;
+static_assert(AT_LOC_DOUBLES < 65536, "entry codes are 16-bit indices into the table");
 
 // Per-tile header at the start of the tile's "big" blob.  160 bytes (a multiple of 16: TMA granularity).
 struct AsmTileHdr {
@@ -80,9 +87,9 @@ __device__ __forceinline__ int sym_index(int a, int b) {          // a, b in 0..
 }
 
 // ------------------------------------------------------------------------------------------------ the hot kernel
-constexpr int AT_SMEM_LOC = AT_NSYM * AT_ECAP * 8;                 // 48384
+constexpr int AT_SMEM_LOC = (AT_LOC_DOUBLES * 8 + 15) / 16 * 16;       // 50608
 constexpr int AT_SMEM_COORD = 2 * AT_VCAP * 16;                    // 8192
-constexpr int AT_SMEM_DIAG = AT_THREADS * 8;                       // 2048
+constexpr int AT_SMEM_DIAG = 0;                                    // (the diagonals live in the loc table)
 constexpr int AT_SMEM_BIG = 2 * AT_BIG_MAX;                        // 37184
 constexpr int AT_SMEM_GEO = 3 * AT_GEO_MAX;                        // 6576
 constexpr int AT_SMEM_TAIL = 512;                                  // barriers + run tables
@@ -150,7 +157,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *loc = reinterpret_cast<double *>(smem_raw);
     double2 *coords = reinterpret_cast<double2 *>(smem_raw + AT_SMEM_LOC);                 // [2][AT_VCAP]
-    double *s_diag = reinterpret_cast<double *>(smem_raw + AT_SMEM_LOC + AT_SMEM_COORD);
     unsigned char *s_big = smem_raw + AT_SMEM_LOC + AT_SMEM_COORD + AT_SMEM_DIAG;          // [2][AT_BIG_MAX]
     unsigned char *s_geo = s_big + AT_SMEM_BIG;                                            // [3][AT_GEO_MAX]
     unsigned char *tail = s_geo + AT_SMEM_GEO;
@@ -169,6 +175,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
         mbar_init(&bar_big[0], 1); mbar_init(&bar_big[1], 1);
         mbar_init(&bar_geo[0], 1); mbar_init(&bar_geo[1], 1); mbar_init(&bar_geo[2], 1);
         mbar_fence_init();
+        loc[AT_ZERO] = 0.0;
     }
     __syncthreads();
 
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
             const double2 *cx = coords + bs * AT_VCAP;
             for (int e = tid; e < nelem; e += AT_THREADS) {
                 const uchar4 tv = etri[e];
-                morley_local_sym(cx[tv.x], cx[tv.y], cx[tv.z], ca, cb, loc + e, AT_ECAP);
+                morley_local_sym(cx[tv.x], cx[tv.y], cx[tv.z], ca, cb, loc + e, AT_LSTRIDE);
             }
         }
         mbar_wait(&bar_big[bs], (uint32_t)((j / 2) & 1));
@@ -267,30 +274,32 @@ __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
                 if (tid >= (int)H->jds_cnt[q]) break;                               // rows are sorted by element count
                 d += loc[dcodes[jds_off[q] + tid]];
             }
-            s_diag[tid] = d;
+            loc[AT_DIAG_BASE + tid] = d;
         }
         __syncthreads();                                                            // [B]
         // ---- phase 2: one destination entry per thread and step, written straight into the CSR
         {
-            int r = 0;
+            int r = 0, es0 = 0, es1 = run_es[1], rs0 = 0;                           // the current run lives in registers
+            uint32_t len = H->run_len[0], magic = run_magic[0];
             for (int i = tid; i < nentries; i += AT_THREADS) {
-                while (i >= run_es[r + 1]) ++r;                                     // i only grows: a forward scan
-                const int within = i - run_es[r];
-                const uint32_t len = H->run_len[r];
-                const int rr = len > 1 ? (int)__umulhi((uint32_t)within, run_magic[r]) : within;
-                const int row = run_rs[r] + rr;
+                while (i >= es1) {                                                  // i only grows: a forward scan
+                    ++r;
+                    es0 = es1; es1 = run_es[r + 1]; rs0 = run_rs[r];
+                    len = H->run_len[r]; magic = run_magic[r];
+                }
+                const int within = i - es0;
+                const int rr = len > 1 ? (int)__umulhi((uint32_t)within, magic) : within;
+                const int row = rs0 + rr;
                 const int k = within - rr * (int)len;
                 const uint32_t c = codes[i];
-                const uint32_t lo = c & 0xFFFFu, hi = c >> 16;
-                double v = lo == AT_DIAG ? s_diag[row] : (lo == AT_NONE ? 0.0 : loc[lo]);
-                if (hi != AT_NONE) v += loc[hi];
+                double v = loc[c & 0xFFFFu] + loc[c >> 16];                         // second = AT_ZERO when there is none
                 double *dst = values + row_out[row] + k;
                 if (accumulate) v += *dst;
                 *dst = v;
             }
         }
         cp_async_wait_all();             // next tile's coordinates have landed
-        __syncthreads();                 // [C] loc, s_diag, this tile's stages and tables are free again
+        __syncthreads();                 // [C] loc, this tile's stages and tables are free again
     }
 }
 
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
     // padding words (never consumed, but the TMA copies them: keep them defined)
     if (tid == 0) {
         if (nr & 1) g_row_out[nr] = 0;
-        for (int i = nentries; i < pad_to(nentries, 4); ++i) g_codes[i] = (AT_NONE << 16) | AT_NONE;
+        for (int i = nentries; i < pad_to(nentries, 4); ++i) g_codes[i] = ((uint32_t)AT_ZERO << 16) | (uint32_t)AT_ZERO;
         for (int i = npairs; i < pad_to(npairs, 8); ++i) g_dcodes[i] = 0;
     }
     // jagged-diagonal offsets of the diagonal lists
@@ -515,24 +524,24 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
         const int len = s_len[tid], np = s_np[tid];
         g_row_out[tid] = doff;
         uint16_t lo[AT_MAXLEN], hi[AT_MAXLEN];
-        for (int s = 0; s < len; ++s) { lo[s] = (uint16_t)AT_NONE; hi[s] = (uint16_t)AT_NONE; }
+        for (int s = 0; s < len; ++s) { lo[s] = (uint16_t)AT_ZERO; hi[s] = (uint16_t)AT_ZERO; }
         bool bad = false;
         for (int q = 0; q < np; ++q) {
             const int32_t code = r2e_idx[my_ptr + q];
             const int64_t el = code >> 3;
             const int li = code & 7;
             const int eloc = bsearch_u32(s_uelem, nelem, (uint32_t)el);
-            g_dcodes[s_scr[q] + tid] = (uint16_t)(sym_index(li, li) * AT_ECAP + eloc);
+            g_dcodes[s_scr[q] + tid] = (uint16_t)(sym_index(li, li) * AT_LSTRIDE + eloc);
             for (int lj = 0; lj < 6; ++lj) {
                 const int32_t c = edofs[(int64_t)lj * nt + el];
                 int s = -1;
                 for (int k = 0; k < len; ++k)
                     if (dst_col[doff + k] == c) { s = k; break; }
                 if (s < 0) continue;                                    // column not kept by the destination layout
-                if (c == my_dof) { lo[s] = (uint16_t)AT_DIAG; continue; }
-                const uint16_t w = (uint16_t)(sym_index(li, lj) * AT_ECAP + eloc);
-                if (lo[s] == (uint16_t)AT_NONE) lo[s] = w;
-                else if (hi[s] == (uint16_t)AT_NONE) hi[s] = w;
+                if (c == my_dof) { lo[s] = (uint16_t)(AT_DIAG_BASE + tid); continue; }
+                const uint16_t w = (uint16_t)(sym_index(li, lj) * AT_LSTRIDE + eloc);
+                if (lo[s] == (uint16_t)AT_ZERO) lo[s] = w;
+                else if (hi[s] == (uint16_t)AT_ZERO) hi[s] = w;
                 else bad = true;                                        // three triangles on one edge: not a manifold mesh
             }
         }
