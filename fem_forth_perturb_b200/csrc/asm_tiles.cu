@@ -56,16 +56,21 @@ constexpr int AT_ZERO = AT_DIAG_BASE + AT_THREADS;        // loc[AT_ZERO] = 0.0:
 constexpr int AT_LOC_DOUBLES = AT_ZERO + 1;
 static_assert(AT_LOC_DOUBLES < 65536, "entry codes are 16-bit indices into the table");
 
-// Per-tile header at the start of the tile's "big" blob.  160 bytes (a multiple of 16: TMA granularity).
+// Per-tile header at the start of the tile's "big" blob.  288 bytes (a multiple of 16: TMA granularity).  Rows of a
+// tile are sorted by (element count, length) descending; a RUN is a maximal sequence of rows of equal length, so an
+// entry index maps to (row, position) by one multiply-high with the run's magic number ceil(2^32 / length).
 struct AsmTileHdr {
     int32_t nrows, nentries, npairs, nruns;
     int32_t npq, pad0, pad1, pad2;                // npq = largest number of elements of a row
-    uint16_t run_rows[AT_MAXRUNS];                // rows in run r (rows of a run have the same length)
-    uint16_t jds_cnt[AT_MAXP];                    // rows with more than q elements (rows are sorted by that count)
+    uint32_t run_magic[AT_MAXRUNS];               // ceil(2^32 / run_len) (0 for length 1)
+    uint16_t run_es[AT_MAXRUNS + 2];              // first entry of run r; run_es[r >= nruns] = nentries
+    uint16_t run_rs[AT_MAXRUNS + 2];              // first row of run r
+    uint16_t jds_off[AT_MAXP + 2];                // diagonal lists, jagged-diagonal layout: offset of the q-th elements
+    uint16_t jds_cnt[AT_MAXP];                    // rows with more than q elements
     uint8_t run_len[AT_MAXRUNS];                  // entries per row in run r
-    uint8_t pad3[48];
+    uint8_t pad3[36];
 };
-static_assert(sizeof(AsmTileHdr) == 160, "header layout");
+static_assert(sizeof(AsmTileHdr) == 288, "header layout");
 
 // big blob  = [AsmTileHdr][row_out: pad2(nrows) x int64][codes: pad4(nentries) x uint32][dcodes: pad8(npairs) x uint16]
 // geo blob  = [nvert, nelem, 0, 0 : int32][vlist: pad4(nvert) x uint32][etri: pad4(nelem) x uchar4]
@@ -74,7 +79,7 @@ __host__ __device__ inline int big_bytes(int nrows, int nentries, int npairs) {
     return (int)sizeof(AsmTileHdr) + pad_to(nrows, 2) * 8 + pad_to(nentries, 4) * 4 + pad_to(npairs, 8) * 2;
 }
 __host__ __device__ inline int geo_bytes(int nvert, int nelem) { return 16 + pad_to(nvert, 4) * 4 + pad_to(nelem, 4) * 4; }
-constexpr int AT_BIG_MAX = 160 + AT_THREADS * 8 + AT_NCAP * 4 + AT_DCAP * 2;      // 18592
+constexpr int AT_BIG_MAX = 288 + AT_THREADS * 8 + AT_NCAP * 4 + AT_DCAP * 2;      // 18720
 constexpr int AT_GEO_MAX = 16 + AT_VCAP * 4 + AT_ECAP * 4;                        // 2192
 
 // Tile table entry (what the producer thread reads one tile ahead): blob offsets in bytes.
@@ -90,9 +95,9 @@ __device__ __forceinline__ int sym_index(int a, int b) {          // a, b in 0..
 constexpr int AT_SMEM_LOC = (AT_LOC_DOUBLES * 8 + 15) / 16 * 16;       // 50608
 constexpr int AT_SMEM_COORD = 2 * AT_VCAP * 16;                    // 8192
 constexpr int AT_SMEM_DIAG = 0;                                    // (the diagonals live in the loc table)
-constexpr int AT_SMEM_BIG = 2 * AT_BIG_MAX;                        // 37184
+constexpr int AT_SMEM_BIG = 2 * AT_BIG_MAX;                        // 37440
 constexpr int AT_SMEM_GEO = 3 * AT_GEO_MAX;                        // 6576
-constexpr int AT_SMEM_TAIL = 512;                                  // barriers + run tables
+constexpr int AT_SMEM_TAIL = 64;                                   // barriers
 constexpr int AT_SMEM_BYTES = AT_SMEM_LOC + AT_SMEM_COORD + AT_SMEM_DIAG + AT_SMEM_BIG + AT_SMEM_GEO + AT_SMEM_TAIL;
 static_assert(AT_BIG_MAX % 16 == 0 && AT_GEO_MAX % 16 == 0, "stage alignment");
 
@@ -150,9 +155,10 @@ __device__ __forceinline__ void morley_local_sym(double2 x0, double2 x1, double2
     loc[20 * stride] = ca * E22 + third;
 }
 
+template <bool ACC>
 __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
     int64_t ntiles, const AsmTileRef *__restrict__ tiles, const unsigned char *__restrict__ big,
-    const unsigned char *__restrict__ geo, const double2 *__restrict__ pxy, double ca, double cb, int accumulate,
+    const unsigned char *__restrict__ geo, const double2 *__restrict__ pxy, double ca, double cb,
     double *__restrict__ values) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *loc = reinterpret_cast<double *>(smem_raw);
@@ -162,10 +168,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
     unsigned char *tail = s_geo + AT_SMEM_GEO;
     uint64_t *bar_big = reinterpret_cast<uint64_t *>(tail);            // [2]
     uint64_t *bar_geo = reinterpret_cast<uint64_t *>(tail + 16);       // [3]
-    int32_t *run_es = reinterpret_cast<int32_t *>(tail + 64);          // [AT_MAXRUNS + 1] first entry of run r
-    int32_t *run_rs = reinterpret_cast<int32_t *>(tail + 64 + 80);     // [AT_MAXRUNS + 1] first row of run r
-    uint32_t *run_magic = reinterpret_cast<uint32_t *>(tail + 64 + 160);   // [AT_MAXRUNS] ceil(2^32 / len)
-    int32_t *jds_off = reinterpret_cast<int32_t *>(tail + 64 + 240);   // [AT_MAXP + 1]
 
     const int tid = threadIdx.x;
     const int64_t G = gridDim.x;
@@ -242,59 +244,75 @@ __global__ void __launch_bounds__(AT_THREADS, 2) k_assemble_morley_tiles(
         mbar_wait(&bar_big[bs], (uint32_t)((j / 2) & 1));
         const unsigned char *B = s_big + bs * AT_BIG_MAX;
         const AsmTileHdr *H = reinterpret_cast<const AsmTileHdr *>(B);
-        const int nrows = H->nrows, nentries = H->nentries, nruns = H->nruns, npq = H->npq;
+        const int nrows = H->nrows, nentries = H->nentries, npq = H->npq;
         const int64_t *row_out = reinterpret_cast<const int64_t *>(B + sizeof(AsmTileHdr));
         const uint32_t *codes = reinterpret_cast<const uint32_t *>(B + sizeof(AsmTileHdr) + pad_to(nrows, 2) * 8);
         const uint16_t *dcodes = reinterpret_cast<const uint16_t *>(B + sizeof(AsmTileHdr) + pad_to(nrows, 2) * 8 +
                                                                      pad_to(nentries, 4) * 4);
-        if (tid == 0) {                                                             // run / jagged-diagonal tables
-            int es = 0, rs = 0;
-            for (int r = 0; r < nruns; ++r) {
-                run_es[r] = es; run_rs[r] = rs;
-                const uint32_t len = H->run_len[r];
-                run_magic[r] = len > 1 ? (uint32_t)(0xFFFFFFFFu / len) + 1u : 0u;   // len 1: handled without the multiply
-                es += (int)len * H->run_rows[r];
-                rs += H->run_rows[r];
-            }
-            run_es[nruns] = es; run_rs[nruns] = rs;
-            int o = 0;
-            for (int q = 0; q < npq; ++q) { jds_off[q] = o; o += H->jds_cnt[q]; }
-            jds_off[npq] = o;
-        }
-        __syncthreads();                                                            // [A] loc + tables complete
+        __syncthreads();                                                            // [A] the tile's local matrices are complete
         // ---- next tile's vertex coordinates: in flight during phases D and 2
         if (have_next) {
             mbar_wait(&bar_geo[(j + 1) % 3], (uint32_t)(((j + 1) / 3) & 1));
             gather_coords((j + 1) % 3, bs ^ 1);
         }
-        // ---- phase D: the diagonal of every row (its elements in ascending element id)
+        // ---- phase D: the diagonal of every row (its elements in ascending element id).  All table reads of a row
+        //      are issued before the first add; rows shorter than the tile's longest read the zero slot.
         if (tid < nrows) {
             double d = 0.0;
-            for (int q = 0; q < npq; ++q) {
-                if (tid >= (int)H->jds_cnt[q]) break;                               // rows are sorted by element count
-                d += loc[dcodes[jds_off[q] + tid]];
+            for (int q0 = 0; q0 < npq; q0 += 8) {
+                uint32_t dc[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int q = q0 + u;
+                    dc[u] = (q < npq && tid < (int)H->jds_cnt[q]) ? (uint32_t)dcodes[H->jds_off[q] + tid] : (uint32_t)AT_ZERO;
+                }
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = loc[dc[u]];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d += v[u];
             }
             loc[AT_DIAG_BASE + tid] = d;
         }
         __syncthreads();                                                            // [B]
-        // ---- phase 2: one destination entry per thread and step, written straight into the CSR
+        // ---- phase 2: one destination entry per thread and step, written straight into the CSR.  Two entries per
+        //      iteration so that two independent chains (code -> two table reads -> add -> store) are in flight.
         {
-            int r = 0, es0 = 0, es1 = run_es[1], rs0 = 0;                           // the current run lives in registers
-            uint32_t len = H->run_len[0], magic = run_magic[0];
-            for (int i = tid; i < nentries; i += AT_THREADS) {
+            int r = 0, es0 = 0, es1 = H->run_es[1], rs0 = 0;                        // the current run lives in registers
+            uint32_t len = H->run_len[0], magic = H->run_magic[0];
+            auto locate = [&](int i, int &row, int &k) {
                 while (i >= es1) {                                                  // i only grows: a forward scan
                     ++r;
-                    es0 = es1; es1 = run_es[r + 1]; rs0 = run_rs[r];
-                    len = H->run_len[r]; magic = run_magic[r];
+                    es0 = es1; es1 = H->run_es[r + 1]; rs0 = H->run_rs[r];
+                    len = H->run_len[r]; magic = H->run_magic[r];
                 }
                 const int within = i - es0;
                 const int rr = len > 1 ? (int)__umulhi((uint32_t)within, magic) : within;
-                const int row = rs0 + rr;
-                const int k = within - rr * (int)len;
+                row = rs0 + rr;
+                k = within - rr * (int)len;
+            };
+            int i = tid;
+            for (; i + AT_THREADS < nentries; i += 2 * AT_THREADS) {
+                int rowA, kA, rowB, kB;
+                locate(i, rowA, kA);
+                locate(i + AT_THREADS, rowB, kB);
+                const uint32_t cA = codes[i], cB = codes[i + AT_THREADS];
+                const double a0 = loc[cA & 0xFFFFu], a1 = loc[cA >> 16];            // second = AT_ZERO when there is none
+                const double b0 = loc[cB & 0xFFFFu], b1 = loc[cB >> 16];
+                double *dA = values + row_out[rowA] + kA;
+                double *dB = values + row_out[rowB] + kB;
+                double vA = a0 + a1, vB = b0 + b1;
+                if (ACC) { vA += *dA; vB += *dB; }
+                *dA = vA;
+                *dB = vB;
+            }
+            if (i < nentries) {
+                int row, k;
+                locate(i, row, k);
                 const uint32_t c = codes[i];
-                double v = loc[c & 0xFFFFu] + loc[c >> 16];                         // second = AT_ZERO when there is none
+                double v = loc[c & 0xFFFFu] + loc[c >> 16];
                 double *dst = values + row_out[row] + k;
-                if (accumulate) v += *dst;
+                if (ACC) v += *dst;
                 *dst = v;
             }
         }
@@ -374,6 +392,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
     __shared__ int32_t s_scr[PB_PAIRCAP + 1];
     __shared__ int32_t s_bad;
     __shared__ AsmTileHdr s_hdr;
+    __shared__ int32_t s_run_rows[AT_MAXRUNS];
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -412,21 +431,41 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
             if (i == 0 || s_len[i] != s_len[i - 1]) {
                 if (nruns == AT_MAXRUNS) { s_bad = PB_SPLIT; break; }
                 s_hdr.run_len[nruns] = (uint8_t)s_len[i];
-                s_hdr.run_rows[nruns] = 0;
+                s_run_rows[nruns] = 0;
                 ++nruns;
             }
-            ++s_hdr.run_rows[nruns - 1];
+            ++s_run_rows[nruns - 1];
         }
-        for (int r = nruns; r < AT_MAXRUNS; ++r) { s_hdr.run_len[r] = 0; s_hdr.run_rows[r] = 0; }
+        for (int r = nruns; r < AT_MAXRUNS; ++r) { s_hdr.run_len[r] = 0; s_run_rows[r] = 0; }
+        {
+            int es = 0, rs = 0;
+            for (int r = 0; r < AT_MAXRUNS + 2; ++r) {
+                s_hdr.run_es[r] = (uint16_t)es; s_hdr.run_rs[r] = (uint16_t)rs;
+                if (r < nruns) {
+                    const uint32_t len = s_hdr.run_len[r];
+                    s_hdr.run_magic[r] = len > 1 ? (uint32_t)(0xFFFFFFFFu / len) + 1u : 0u;
+                    es += (int)len * s_run_rows[r];
+                    rs += s_run_rows[r];
+                } else if (r < AT_MAXRUNS) {
+                    s_hdr.run_magic[r] = 0u;
+                }
+            }
+        }
         const int npq = nr ? s_np[0] : 0;
-        for (int q = 0; q < AT_MAXP; ++q) {
-            int c = 0;
-            for (int i = 0; i < nr; ++i) c += s_np[i] > q;
-            s_hdr.jds_cnt[q] = (uint16_t)c;
+        {
+            int o = 0;
+            for (int q = 0; q < AT_MAXP + 2; ++q) {
+                int c = 0;
+                if (q < AT_MAXP)
+                    for (int i = 0; i < nr; ++i) c += s_np[i] > q;
+                s_hdr.jds_off[q] = (uint16_t)o;
+                if (q < AT_MAXP) s_hdr.jds_cnt[q] = (uint16_t)c;
+                o += c;
+            }
         }
         s_hdr.nrows = nr; s_hdr.nentries = eo; s_hdr.npairs = po; s_hdr.nruns = nruns; s_hdr.npq = npq;
         s_hdr.pad0 = s_hdr.pad1 = s_hdr.pad2 = 0;
-        for (int i = 0; i < 48; ++i) s_hdr.pad3[i] = 0;
+        for (int i = 0; i < 36; ++i) s_hdr.pad3[i] = 0;
         if (po > AT_DCAP || eo > AT_NCAP || po > PB_PAIRCAP) s_bad = PB_SPLIT;
     }
     __syncthreads();
@@ -484,7 +523,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
     const AsmTileRef ref = tiles[tile];
     unsigned char *Bg = big + ref.big_off;
     unsigned char *Gg = geo + ref.geo_off;
-    {   // header (160 bytes = 40 words)
+    {   // header
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_hdr);
         uint32_t *dst = reinterpret_cast<uint32_t *>(Bg);
         for (int i = tid; i < (int)(sizeof(AsmTileHdr) / 4); i += AT_THREADS) dst[i] = src[i];
@@ -513,11 +552,6 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
         for (int i = nentries; i < pad_to(nentries, 4); ++i) g_codes[i] = ((uint32_t)AT_ZERO << 16) | (uint32_t)AT_ZERO;
         for (int i = npairs; i < pad_to(npairs, 8); ++i) g_dcodes[i] = 0;
     }
-    // jagged-diagonal offsets of the diagonal lists
-    if (tid == 0) {
-        int o = 0;
-        for (int q = 0; q < AT_MAXP; ++q) { s_scr[q] = o; o += s_hdr.jds_cnt[q]; }
-    }
     __syncthreads();
     if (tid < nr) {
         const int64_t doff = dst_off[r0 + orig];
@@ -531,7 +565,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_plan_tiles(
             const int64_t el = code >> 3;
             const int li = code & 7;
             const int eloc = bsearch_u32(s_uelem, nelem, (uint32_t)el);
-            g_dcodes[s_scr[q] + tid] = (uint16_t)(sym_index(li, li) * AT_LSTRIDE + eloc);
+            g_dcodes[s_hdr.jds_off[q] + tid] = (uint16_t)(sym_index(li, li) * AT_LSTRIDE + eloc);
             for (int lj = 0; lj < 6; ++lj) {
                 const int32_t c = edofs[(int64_t)lj * nt + el];
                 int s = -1;
@@ -659,16 +693,22 @@ extern "C" int mwx_assemble_morley_plan(const mwx_asm_plan_t *p, const double *p
     cudaStream_t st = as_stream(stream);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_tiles<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MWX_CUDA(cudaFuncSetAttribute(k_assemble_morley_tiles<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int occ = 0;
-        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble_morley_tiles, AT_THREADS, AT_SMEM_BYTES));
+        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble_morley_tiles<false>, AT_THREADS, AT_SMEM_BYTES));
         ctas_per_sm = occ > 0 ? occ : 1;
     }
     const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     const unsigned grid = (unsigned)(p->ntiles < cap ? p->ntiles : cap);
-    k_assemble_morley_tiles<<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(p->ntiles, p->tiles, p->big, p->geo,
-                                                                     (const double2 *)pxy, ca, cb, accumulate, values);
+    if (accumulate)
+        k_assemble_morley_tiles<true><<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(p->ntiles, p->tiles, p->big, p->geo,
+                                                                               (const double2 *)pxy, ca, cb, values);
+    else
+        k_assemble_morley_tiles<false><<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(p->ntiles, p->tiles, p->big, p->geo,
+                                                                                (const double2 *)pxy, ca, cb, values);
     MWX_LAUNCH_CHECK();
     return 0;
 }

@@ -484,6 +484,7 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
              int64_t *first_hit_host) {
     Scratch<CgScalars> sc(st);
     int rechecks = 0;
+    int64_t floor_it = 0;
     if (first_hit_host) *first_hit_host = 0;
     Scratch<double> partials(st);
     MWX_CUDA(sc.alloc(1));
@@ -554,6 +555,18 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
                 *info_host = (int32_t)(it < 0x7fffffff ? it : 0x7fffffff);
                 return 0;
             }
+            if (max_rechecks > 0 && floor_it == 0) floor_it = it;
+        }
+        // ... or 10 iterations after the first failed re-check: from the recomputed residual the recurrence often
+        // hovers just above the threshold and never asks for another re-check
+        if (max_rechecks > 0 && floor_it > 0 && it >= floor_it + 10) {
+            rc = launch_residual(n, indptr, indices, values, x, b, r, jacobi ? dinv : nullptr, sc.p, partials.p, st);
+            if (rc) return rc;
+            MWX_CUDA(cudaMemcpyAsync(h, &sc.p->rr, sizeof(double), cudaMemcpyDeviceToHost, st));
+            MWX_CUDA(cudaStreamSynchronize(st));
+            *resid_host = sqrt(h[0]);
+            *info_host = *resid_host <= atol ? 0 : (int32_t)(it < 0x7fffffff ? it : 0x7fffffff);
+            return 0;
         }
     }
     *info_host = (int32_t)(maxiter < 0x7fffffff ? maxiter : 0x7fffffff);

@@ -274,7 +274,8 @@ int mwx_pcg_amg(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_
 
 /* Same solve with two diagnostics that scipy's cg does not have (both off = mwx_pcg_amg): *first_hit_host = the first
  * iteration whose recurrence residual met the tolerance; max_rechecks > 0 stops after that many FAILED true-residual
- * re-checks (info = iteration count, *resid_host = the true residual) instead of iterating to maxiter - on very fine
+ * re-checks, or 10 iterations after the first one (info = iteration count, *resid_host = the true residual), instead
+ * of iterating to maxiter - on very fine
  * meshes eps_mach ||A|| ||x|| exceeds tol ||b|| and the scipy 1.4.1 rule can never be met in fp64. */
 int mwx_pcg_amg_monitored(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_t *indices,
                           const double *values, const double *b, double *x, double tol, int64_t maxiter,
