@@ -129,16 +129,17 @@ def run_penalty(refine_time=7, epsilons=(1, 1e-2, 1e-4, 1e-6), element_type='P1'
 
 
 def solve_problem1(m, epsilon, f_load, element_type='P1', solver_type='mgcg', intorder=5, tol=1e-8, mode='parity',
-                   iters=None):
+                   iters=None, maxiter=None):
     """ref main/example1/run.py:182-222 with the B200 package."""
     element = {'w': ElementTriP1() if element_type == 'P1' else ElementTriP2(), 'u': ElementTriMorley()}
     basis = {v: InteriorBasis(m, e, intorder=intorder) for v, e in element.items()}
 
     def make_solver():
+        kw = {} if maxiter is None else {'maxiter': maxiter}       # ref main/example1/test/test_solver.py: maxiter=1000
         if solver_type == 'mgcg':
-            return solver_iter_mgcg(tol=tol, mode=mode)
+            return solver_iter_mgcg(tol=tol, mode=mode, **kw)
         if solver_type == 'pcg':
-            return solver_iter_krylov(Precondition=True, tol=tol)
+            return solver_iter_krylov(Precondition=True, tol=tol, **kw)
         raise Exception("Solver not supported")
 
     K1 = asm(laplace, basis['w'])
@@ -155,7 +156,7 @@ def solve_problem1(m, epsilon, f_load, element_type='P1', solver_type='mgcg', in
 
 
 def run(refine_time=6, epsilon_range=6, element_type='P2', solver_type='mgcg', intorder=5, tol=1e-8, mode='parity',
-        out=print):
+        out=print, maxiter=None):
     """Returns {epsilon: array (refine_time, 4) of L2, H1, H2, Energy} and prints the reference's tables."""
     results, iteration_log = {}, {}
     t0 = time.time()
@@ -166,7 +167,7 @@ def run(refine_time=6, epsilon_range=6, element_type='P2', solver_type='mgcg', i
         rows, its = [], []
         for i in range(1, refine_time + 1):
             m.refine()
-            uh0, basis = solve_problem1(m, epsilon, f_load, element_type, solver_type, intorder, tol, mode, its)
+            uh0, basis = solve_problem1(m, epsilon, f_load, element_type, solver_type, intorder, tol, mode, its, maxiter)
             L2u, Du, D2u = morley_error_norms(basis['u'], uh0, exact_u, dexact_u, ddexact)
             epu = np.sqrt(epsilon ** 2 * D2u ** 2 + Du ** 2)
             rows.append((L2u, L2u + Du, L2u + Du + D2u, epu))

@@ -13,7 +13,7 @@ from .basis import (ElementTriMorley, ElementTriP1, ElementTriP2,        # noqa:
 from .forms import (BilinearFormGPU, a_load, b_load, penalty_1,          # noqa: F401
                     penalty_2, penalty_3, laplace, wv_load, mass, LinearForm, LinearFormGPU, as_form)
 from .assembly import (asm_gpu, asm, DeviceCSR, MixedAction, morley_error_norms,   # noqa: F401
-                       morley_facet_pnv, project, assembly_kernel_name, TilePlan, hilbert_order)
+                       morley_facet_pnv, morley_nested_error_norms, project, assembly_kernel_name, TilePlan, hilbert_order)
 from .problems import Problem                                            # noqa: F401
 from .solvers import (solver_iter_krylov, solver_iter_krylov_iter,       # noqa: F401
                       solver_iter_pcg, solver_iter_mgcg, solver_iter_mgcg_iter, solver_iter_pyamg,
@@ -21,6 +21,6 @@ from .solvers import (solver_iter_krylov, solver_iter_krylov_iter,       # noqa:
 
 __all__ = ['MeshTri', 'ElementTriMorley', 'ElementTriP1', 'ElementTriP2', 'InteriorBasis', 'FacetBasis',
            'a_load', 'b_load', 'penalty_1', 'penalty_2', 'penalty_3', 'laplace', 'wv_load', 'LinearForm', 'asm_gpu', 'asm',
-           'DeviceCSR', 'MixedAction', 'morley_error_norms', 'morley_facet_pnv', 'project', 'mass',
+           'DeviceCSR', 'MixedAction', 'morley_error_norms', 'morley_facet_pnv', 'morley_nested_error_norms', 'project', 'mass',
            'solver_iter_krylov', 'solver_iter_krylov_iter', 'solver_iter_pcg', 'solver_iter_mgcg',
            'solver_iter_mgcg_iter', 'solver_iter_pyamg', 'build_pc_diag', 'solve', 'condense', 'CondensePlan', 'AMGHierarchy', 'pcg', 'MwxError', 'Problem']

@@ -35,6 +35,7 @@ _SIGNATURES = {
     'mwx_morley_error_sums_problem': [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp],
     'mwx_wv_action': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_morley_error_sums': [i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_morley_sample_nested': [i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp],
     'mwx_assemble_morley_mass': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_morley_load_vector': [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_morley_facet_pnv': [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp],

@@ -421,6 +421,30 @@ def morley_error_norms(basis, uh, exact_u=None, dexact_u=None, ddexact=None, pro
     return float(s[0]), float(s[1]), float(s[2])
 
 
+def morley_nested_error_norms(base_basis, u_base, coarse_basis, u_coarse):
+    """(L2, D1, D2) of u^N - u_h for a level-N solution and a solution of a coarser mesh of the same uniform
+    refinement family, at the quadrature points of the level-N mesh (ref main/example2/run.py:101-172: the
+    per-point ``interpolator`` loops and the DG-P1 / DG-P0 ``project`` chain - exact for a piecewise quadratic, so
+    they reduce to sampling u_h and its elementwise derivatives).  One sampling kernel + the error-sum kernel."""
+    torch = L.require_cuda()
+    mf, mc = base_basis.mesh, coarse_basis.mesh
+    dev = mf.device
+    as_dev = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev) if isinstance(v, np.ndarray) else v
+    uN, uc = as_dev(u_base), as_dev(u_coarse)
+    _, W = base_basis.quadrature()
+    nq = len(W)
+    samples = torch.empty(6 * mf.nt * nq, dtype=torch.float64, device=dev)
+    L.check(L.lib().mwx_morley_sample_nested(mf.nt, nq, L.ptr(base_basis.d_quadrature()), L.ptr(mf.d_pxy), L.ptr(mf.d_t),
+                                             mc.nt, L.ptr(mc.d_pxy), L.ptr(mc.d_t), L.ptr(coarse_basis.d_element_dofs),
+                                             L.ptr(uc), L.ptr(samples), L.stream()), 'mwx_morley_sample_nested')
+    sums = torch.empty(3, dtype=torch.float64, device=dev)
+    L.check(L.lib().mwx_morley_error_sums(mf.nt, nq, L.ptr(base_basis.d_quadrature()), L.ptr(mf.d_pxy), L.ptr(mf.d_t),
+                                          L.ptr(base_basis.d_element_dofs), L.ptr(uN), L.ptr(samples), L.ptr(sums),
+                                          L.stream()), 'mwx_morley_error_sums')
+    s = np.sqrt(sums.cpu().numpy())
+    return float(s[0]), float(s[1]), float(s[2])
+
+
 def morley_facet_pnv(fbasis, uh):
     """``L2pnvError.assemble(fbasis, w=fbasis.interpolate(uh0))`` (ref main/example1/run.py:106-108,527):
     sum over the boundary facets of int_F (h_F n . grad u_h)^2."""

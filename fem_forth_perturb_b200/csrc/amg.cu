@@ -19,27 +19,10 @@
 #include <new>
 #include <vector>
 
-#include "krylov.cuh"
+#include "amg_dev.cuh"
 
 namespace mwx {
 namespace {
-
-struct DCsr {
-    int64_t rows = 0, cols = 0, nnz = 0;
-    int64_t plan = -1;                         // -(planned SpMV tile height), see spmv_plan_rows
-    int64_t *ptr = nullptr;
-    int32_t *idx = nullptr;
-    double *val = nullptr;
-};
-
-struct DLevel {
-    DCsr A, P, R;
-    double *dinv = nullptr, *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
-    int32_t *ord_f = nullptr, *ord_b = nullptr;
-    int64_t *wp_f = nullptr, *wp_b = nullptr;
-    int64_t nw_f = 0, nw_b = 0;
-    double rho = 0.0;                   // estimate of the spectral radius of D^-1 A
-};
 
 __global__ void __launch_bounds__(1024) k_gs_wavefront_sweep(int64_t nwaves, const int64_t *__restrict__ wave_ptr,
                                                              const int32_t *__restrict__ order,
@@ -130,7 +113,6 @@ int upload_csr(const mwx_amg_host_t *h, int level, int which, DCsr &out, cudaStr
     return 0;
 }
 
-void free_csr(DCsr &m) { cudaFree(m.ptr); cudaFree(m.idx); cudaFree(m.val); m = DCsr(); }
 
 // Symmetric pseudo-inverse by cyclic Jacobi rotations (coarsest level, a handful of rows); cutoff as in
 // scipy 1.4.1 pinv2: singular values below 1e6*eps*max are dropped.
@@ -188,19 +170,13 @@ inline unsigned vgrid(int64_t n) {
 }
 
 }  // namespace
+
+void free_csr(DCsr &m) { cudaFree(m.ptr); cudaFree(m.idx); cudaFree(m.val); m = DCsr(); }
+
 }  // namespace mwx
 
 using namespace mwx;
 
-struct mwx_amg_dev {
-    std::vector<DLevel> lv;
-    double *pinv = nullptr;              // dense (n_last x n_last), row-major
-    int64_t n_last = 0;
-    int smoother = 0, degree = 2;
-    double cheb_ratio = 10.0;
-    CgScalars *sc = nullptr;
-    double *partials = nullptr;
-};
 
 extern "C" int mwx_gs_wavefronts_backward_host(int64_t n, const int64_t *indptr, const int32_t *indices,
                                                int32_t *order, int64_t *wave_ptr, int64_t *nwaves);
@@ -211,6 +187,7 @@ extern "C" void mwx_amg_destroy_dev(mwx_amg_dev_t *d) {
         free_csr(L.A); free_csr(L.P); free_csr(L.R);
         cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.x2); cudaFree(L.b); cudaFree(L.r); cudaFree(L.d);
         cudaFree(L.ord_f); cudaFree(L.ord_b); cudaFree(L.wp_f); cudaFree(L.wp_b);
+        cudaFree(L.roots); cudaFree(L.cand);
     }
     cudaFree(d->pinv); cudaFree(d->sc); cudaFree(d->partials);
     delete d;
@@ -247,6 +224,106 @@ static int estimate_rho(mwx_amg_dev *d, DLevel &L, cudaStream_t st) {
     return 0;
 }
 
+// Everything a hierarchy needs besides its operators (which are already on the device): SpMV plans, work vectors,
+// inverse diagonals, the dense pseudo-inverse of the coarsest operator and the smoother data.
+int mwx::amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_host, cudaStream_t st) {
+    const int nl = (int)d->lv.size();
+    int rc = 0;
+    if (!d->sc) {
+        if (cudaMalloc((void **)&d->sc, sizeof(CgScalars)) != cudaSuccess) return MWX_E_NOMEM;
+        if (cudaMalloc((void **)&d->partials, sizeof(double) * 2 * RED_MAX_BLOCKS) != cudaSuccess) return MWX_E_NOMEM;
+        cudaMemsetAsync(d->sc, 0, sizeof(CgScalars), st);
+    }
+    auto plan = [&](DCsr &M) {
+        if (M.plan != -1 || !M.ptr) return 0;
+        int tile_rows = 0;
+        const int prc = spmv_plan_rows(M.rows, M.ptr, &tile_rows, st);
+        if (!prc) M.plan = -(int64_t)tile_rows;
+        return prc;
+    };
+    for (int l = 0; l < nl; ++l) {
+        DLevel &L = d->lv[(size_t)l];
+        if ((rc = plan(L.A))) return rc;
+        const int64_t n = L.A.rows;
+        if (l + 1 < nl) {
+            if ((rc = plan(L.P)) || (rc = plan(L.R))) return rc;
+            const size_t bytes = sizeof(double) * (size_t)n;
+            if (cudaMalloc((void **)&L.dinv, bytes) != cudaSuccess || cudaMalloc((void **)&L.r, bytes) != cudaSuccess ||
+                cudaMalloc((void **)&L.x2, bytes) != cudaSuccess || cudaMalloc((void **)&L.d, bytes) != cudaSuccess)
+                return MWX_E_NOMEM;
+            if ((rc = launch_csr_diagonal(n, L.A.ptr, L.A.idx, L.A.val, L.dinv, 1, st))) return rc;
+        }
+        if (l > 0) {
+            const size_t bytes = sizeof(double) * (size_t)n;
+            if (cudaMalloc((void **)&L.x, bytes) != cudaSuccess || cudaMalloc((void **)&L.b, bytes) != cudaSuccess)
+                return MWX_E_NOMEM;
+        }
+    }
+    auto download = [&](const DCsr &M, std::vector<int64_t> &ptr, std::vector<int32_t> &idx, std::vector<double> &val) {
+        ptr.resize((size_t)M.rows + 1); idx.resize((size_t)M.nnz); val.resize((size_t)M.nnz);
+        MWX_CUDA(cudaMemcpyAsync(ptr.data(), M.ptr, sizeof(int64_t) * ptr.size(), cudaMemcpyDeviceToHost, st));
+        MWX_CUDA(cudaMemcpyAsync(idx.data(), M.idx, sizeof(int32_t) * idx.size(), cudaMemcpyDeviceToHost, st));
+        MWX_CUDA(cudaMemcpyAsync(val.data(), M.val, sizeof(double) * val.size(), cudaMemcpyDeviceToHost, st));
+        MWX_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+    // coarsest level: dense pseudo-inverse
+    {
+        const DCsr &Ac = d->lv[(size_t)nl - 1].A;
+        const int64_t nc = Ac.rows;
+        d->n_last = nc;
+        std::vector<double> pinv;
+        if (coarse_pinv_host) {
+            pinv.assign(coarse_pinv_host, coarse_pinv_host + nc * nc);
+        } else {
+            if (nc > 4096) return MWX_E_CAPACITY;
+            std::vector<int64_t> ptr;
+            std::vector<int32_t> idx;
+            std::vector<double> val, dense((size_t)(nc * nc), 0.0);
+            if ((rc = download(Ac, ptr, idx, val))) return rc;
+            for (int64_t i = 0; i < nc; ++i)
+                for (int64_t k = ptr[(size_t)i]; k < ptr[(size_t)i + 1]; ++k) dense[(size_t)(i * nc + idx[(size_t)k])] += val[(size_t)k];
+            for (int64_t i = 0; i < nc; ++i)                 // symmetrise round-off
+                for (int64_t j = i + 1; j < nc; ++j) {
+                    const double m = 0.5 * (dense[(size_t)(i * nc + j)] + dense[(size_t)(j * nc + i)]);
+                    dense[(size_t)(i * nc + j)] = dense[(size_t)(j * nc + i)] = m;
+                }
+            dense_pinv_sym(nc, dense, pinv);
+        }
+        if ((rc = upload(pinv, &d->pinv, st))) return rc;
+        cudaStreamSynchronize(st);
+    }
+    // smoother data
+    for (int l = 0; l + 1 < nl; ++l) {
+        DLevel &L = d->lv[(size_t)l];
+        const int64_t n = L.A.rows;
+        if (d->smoother == 0) {
+            std::vector<int64_t> ptr;
+            std::vector<int32_t> idx;
+            std::vector<double> val;
+            if ((rc = download(L.A, ptr, idx, val))) return rc;
+            std::vector<int32_t> ord((size_t)n);
+            std::vector<int64_t> wp((size_t)n + 1);
+            int64_t nw = 0;
+            mwx_gs_wavefronts_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
+            wp.resize((size_t)nw + 1);
+            L.nw_f = nw;
+            if ((rc = upload(ord, &L.ord_f, st)) || (rc = upload(wp, &L.wp_f, st))) return rc;
+            cudaStreamSynchronize(st);
+            wp.assign((size_t)n + 1, 0);
+            mwx_gs_wavefronts_backward_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
+            wp.resize((size_t)nw + 1);
+            L.nw_b = nw;
+            if ((rc = upload(ord, &L.ord_b, st)) || (rc = upload(wp, &L.wp_b, st))) return rc;
+            cudaStreamSynchronize(st);
+        } else {
+            if ((rc = estimate_rho(d, L, st))) return rc;
+        }
+    }
+    cudaStreamSynchronize(st);
+    return 0;
+}
+
 extern "C" int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t cheby_degree,
                               const double *coarse_pinv_host, mwx_amg_dev_t **out, void *stream) {
     if (!h || !out || smoother < 0 || smoother > 2) return MWX_E_BADARG;
@@ -260,82 +337,15 @@ extern "C" int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t
     d->lv.resize((size_t)nl);
     int rc = 0;
     auto fail = [&](int code) { mwx_amg_destroy_dev(d); return code; };
-    if (cudaMalloc((void **)&d->sc, sizeof(CgScalars)) != cudaSuccess) return fail(MWX_E_NOMEM);
-    if (cudaMalloc((void **)&d->partials, sizeof(double) * 2 * RED_MAX_BLOCKS) != cudaSuccess) return fail(MWX_E_NOMEM);
-    cudaMemsetAsync(d->sc, 0, sizeof(CgScalars), st);
     for (int l = 0; l < nl; ++l) {
         DLevel &L = d->lv[(size_t)l];
         if ((rc = upload_csr(h, l, 0, L.A, st))) return fail(rc);
-        const int64_t n = L.A.rows;
         if (l + 1 < nl) {
             if ((rc = upload_csr(h, l, 1, L.P, st))) return fail(rc);
             if ((rc = upload_csr(h, l, 2, L.R, st))) return fail(rc);
-            const size_t bytes = sizeof(double) * (size_t)n;
-            if (cudaMalloc((void **)&L.dinv, bytes) != cudaSuccess || cudaMalloc((void **)&L.r, bytes) != cudaSuccess ||
-                cudaMalloc((void **)&L.x2, bytes) != cudaSuccess || cudaMalloc((void **)&L.d, bytes) != cudaSuccess)
-                return fail(MWX_E_NOMEM);
-            if ((rc = launch_csr_diagonal(n, L.A.ptr, L.A.idx, L.A.val, L.dinv, 1, st))) return fail(rc);
-        }
-        if (l > 0) {
-            const size_t bytes = sizeof(double) * (size_t)n;
-            if (cudaMalloc((void **)&L.x, bytes) != cudaSuccess || cudaMalloc((void **)&L.b, bytes) != cudaSuccess)
-                return fail(MWX_E_NOMEM);
         }
     }
-    // coarsest level: dense pseudo-inverse
-    {
-        int64_t dims[3];
-        mwx_amg_level_dims(h, nl - 1, 0, dims);
-        const int64_t nc = dims[0];
-        d->n_last = nc;
-        std::vector<double> pinv;
-        if (coarse_pinv_host) {
-            pinv.assign(coarse_pinv_host, coarse_pinv_host + nc * nc);
-        } else {
-            std::vector<int64_t> ptr((size_t)nc + 1);
-            std::vector<int32_t> idx((size_t)dims[2]);
-            std::vector<double> val((size_t)dims[2]), dense((size_t)(nc * nc), 0.0);
-            mwx_amg_level_copy(h, nl - 1, 0, ptr.data(), idx.data(), val.data());
-            for (int64_t i = 0; i < nc; ++i)
-                for (int64_t k = ptr[(size_t)i]; k < ptr[(size_t)i + 1]; ++k) dense[(size_t)(i * nc + idx[(size_t)k])] += val[(size_t)k];
-            for (int64_t i = 0; i < nc; ++i)                 // symmetrise round-off
-                for (int64_t j = i + 1; j < nc; ++j) {
-                    const double m = 0.5 * (dense[(size_t)(i * nc + j)] + dense[(size_t)(j * nc + i)]);
-                    dense[(size_t)(i * nc + j)] = dense[(size_t)(j * nc + i)] = m;
-                }
-            dense_pinv_sym(nc, dense, pinv);
-        }
-        if ((rc = upload(pinv, &d->pinv, st))) return fail(rc);
-        cudaStreamSynchronize(st);
-    }
-    // smoother data
-    for (int l = 0; l + 1 < nl; ++l) {
-        DLevel &L = d->lv[(size_t)l];
-        const int64_t n = L.A.rows;
-        if (smoother == 0) {
-            std::vector<int64_t> ptr((size_t)n + 1);
-            std::vector<int32_t> idx((size_t)L.A.nnz);
-            std::vector<double> val((size_t)L.A.nnz);
-            mwx_amg_level_copy(h, l, 0, ptr.data(), idx.data(), val.data());
-            std::vector<int32_t> ord((size_t)n);
-            std::vector<int64_t> wp((size_t)n + 1);
-            int64_t nw = 0;
-            mwx_gs_wavefronts_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
-            wp.resize((size_t)nw + 1);
-            L.nw_f = nw;
-            if ((rc = upload(ord, &L.ord_f, st)) || (rc = upload(wp, &L.wp_f, st))) return fail(rc);
-            cudaStreamSynchronize(st);
-            wp.assign((size_t)n + 1, 0);
-            mwx_gs_wavefronts_backward_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
-            wp.resize((size_t)nw + 1);
-            L.nw_b = nw;
-            if ((rc = upload(ord, &L.ord_b, st)) || (rc = upload(wp, &L.wp_b, st))) return fail(rc);
-            cudaStreamSynchronize(st);
-        } else {
-            if ((rc = estimate_rho(d, L, st))) return fail(rc);
-        }
-    }
-    cudaStreamSynchronize(st);
+    if ((rc = amg_finalize_device_levels(d, coarse_pinv_host, st))) return fail(rc);
     *out = d;
     return 0;
 }

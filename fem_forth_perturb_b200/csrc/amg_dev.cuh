@@ -1,0 +1,52 @@
+// Device-resident AMG hierarchy shared by amg.cu (upload of a host hierarchy, V-cycle, PCG) and amg_setup_dev.cu
+// (smoothed-aggregation setup on the device).
+#pragma once
+#include <vector>
+
+#include "krylov.cuh"
+
+namespace mwx {
+
+struct DCsr {
+    int64_t rows = 0, cols = 0, nnz = 0;
+    int64_t plan = -1;                         // -(planned SpMV tile height), see spmv_plan_rows
+    int64_t *ptr = nullptr;
+    int32_t *idx = nullptr;
+    double *val = nullptr;
+};
+
+struct DLevel {
+    DCsr A, P, R;
+    double *dinv = nullptr, *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
+    int32_t *ord_f = nullptr, *ord_b = nullptr;
+    int64_t *wp_f = nullptr, *wp_b = nullptr;
+    int64_t nw_f = 0, nw_b = 0;
+    double rho = 0.0;                   // estimate of the spectral radius of D^-1 A
+    // smoothed-aggregation levels built on the device keep what the partitioned solver asks for
+    int64_t *roots = nullptr;           // first fine DOF of every aggregate (ascending)
+    int64_t nroots = 0;
+    int32_t coarse_per_root = 0;
+    double *cand = nullptr;             // near-nullspace candidates of this level (rows x ncand)
+    int32_t ncand = 0;
+};
+
+void free_csr(DCsr &m);
+
+// Work vectors, inverse diagonals, SpMV plans and (fast smoothers) spectral-radius estimates of every level whose
+// operators are already on the device; dense pseudo-inverse of the coarsest operator (coarse_pinv_host, or computed
+// here by cyclic Jacobi when null - coarsest level of at most a few thousand rows).
+}  // namespace mwx
+
+struct mwx_amg_dev {
+    std::vector<mwx::DLevel> lv;
+    double *pinv = nullptr;              // dense (n_last x n_last), row-major
+    int64_t n_last = 0;
+    int smoother = 0, degree = 2;
+    double cheb_ratio = 10.0;
+    mwx::CgScalars *sc = nullptr;
+    double *partials = nullptr;
+};
+
+namespace mwx {
+int amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_host, cudaStream_t st);
+}

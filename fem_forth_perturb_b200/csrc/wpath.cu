@@ -328,6 +328,60 @@ __global__ void __launch_bounds__(128) k_morley_errors(int64_t nt, int nq, const
     }
 }
 
+// main/example2 (ref main/example2/run.py:101-172): a Morley function of a COARSE mesh sampled at the quadrature points
+// of a FINE mesh obtained from it by uniform refinement.  The children of triangle k sit at k, k + nt, k + 2 nt, k + 3 nt
+// after every refinement (mesh_builder.cu, as skfem), so the coarse triangle holding fine triangle T is T mod nt_c - the
+// reference's one-point-at-a-time ``basis.interpolator(u)(x)`` becomes index arithmetic.  out6 = (u, ux, uy, uxx, uxy, uyy),
+// six arrays of nt_f * nq - the layout k_morley_errors takes for its comparison samples.  *bad counts points that do not
+// lie in the assumed triangle (meshes not nested): the caller turns that into an error.
+__global__ void __launch_bounds__(128) k_morley_sample_nested(int64_t nt_f, int nq, const double *__restrict__ XW,
+                                                              const double2 *__restrict__ pxy_f,
+                                                              const int32_t *__restrict__ t_f, int64_t nt_c,
+                                                              const double2 *__restrict__ pxy_c,
+                                                              const int32_t *__restrict__ t_c,
+                                                              const int32_t *__restrict__ edofs_c,
+                                                              const double *__restrict__ uh_c,
+                                                              double *__restrict__ out6, int *__restrict__ bad) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt_f) return;
+    const int64_t a = e % nt_c;
+    const double2 y0 = pxy_f[t_f[e]], y1 = pxy_f[t_f[nt_f + e]], y2 = pxy_f[t_f[2 * nt_f + e]];
+    const double2 x0 = pxy_c[t_c[a]], x1 = pxy_c[t_c[nt_c + a]], x2 = pxy_c[t_c[2 * nt_c + a]];
+    MorleyFrame F;
+    morley_frame(x0, x1, x2, F);
+    double u[6];
+    for (int j = 0; j < 6; ++j) u[j] = uh_c[edofs_c[(int64_t)j * nt_c + a]];
+    double hxx = 0.0, hxy = 0.0, hyy = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        double c = 0.0;
+        for (int i = 0; i < 6; ++i) c += u[i] * F.B[i][k];
+        c *= 2.0 * F.gam[k];
+        hxx += c * F.n[k].x * F.n[k].x; hxy += c * F.n[k].x * F.n[k].y; hyy += c * F.n[k].y * F.n[k].y;
+    }
+    const double det = (x1.x - x0.x) * (x2.y - x0.y) - (x1.y - x0.y) * (x2.x - x0.x);
+    const int64_t N = nt_f * (int64_t)nq;
+    int nbad = 0;
+    for (int q = 0; q < nq; ++q) {
+        const double xi = XW[q], eta = XW[nq + q];
+        const double px = y0.x + (y1.x - y0.x) * xi + (y2.x - y0.x) * eta - x0.x;
+        const double py = y0.y + (y1.y - y0.y) * xi + (y2.y - y0.y) * eta - x0.y;
+        const double l1 = (px * (x2.y - x0.y) - py * (x2.x - x0.x)) / det;
+        const double l2 = (py * (x1.x - x0.x) - px * (x1.y - x0.y)) / det;
+        const double lam[3] = {1.0 - l1 - l2, l1, l2};
+        nbad += (lam[0] < -1e-9) | (lam[1] < -1e-9) | (lam[2] < -1e-9);
+        double val = 0.0, gx = 0.0, gy = 0.0;
+        for (int i = 0; i < 6; ++i) {
+            val += u[i] * morley_value(F, i, lam);
+            const double2 g = morley_grad(F, i, lam);
+            gx += u[i] * g.x; gy += u[i] * g.y;
+        }
+        const int64_t o = e * nq + q;
+        out6[o] = val; out6[N + o] = gx; out6[2 * N + o] = gy;
+        out6[3 * N + o] = hxx; out6[4 * N + o] = hxy; out6[5 * N + o] = hyy;
+    }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
 // Morley mass matrix rows (project(exact_u, basis_to=basis['u']), ref main/example3/run.py:66 +
 // main/example3/utils.py:494-565): quartic integrand, integrated with the basis' quadrature rule.
 __global__ void __launch_bounds__(128) k_morley_mass(int64_t nrows, int64_t nt, int nq, const double *__restrict__ XW,
@@ -475,6 +529,24 @@ extern "C" int mwx_morley_error_sums_problem(int32_t problem, int64_t nt, int32_
     k_fold3<<<1, 1024, 0, st>>>(nb, partials.p, sums3);
     MWX_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mwx_morley_sample_nested(int64_t nt_f, int32_t nq, const double *xw, const double *pxy_f, const int32_t *t_f,
+                                        int64_t nt_c, const double *pxy_c, const int32_t *t_c, const int32_t *edofs_c,
+                                        const double *uh_c, double *out6, void *stream) {
+    if (nt_f <= 0 || nt_c <= 0 || nt_f % nt_c || nq <= 0 || !xw || !pxy_f || !t_f || !pxy_c || !t_c || !edofs_c || !uh_c || !out6)
+        return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    Scratch<int> bad(st);
+    MWX_CUDA(bad.alloc(1));
+    MWX_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    k_morley_sample_nested<<<grid_for(nt_f, 128), 128, 0, st>>>(nt_f, nq, xw, (const double2 *)pxy_f, t_f, nt_c,
+                                                                 (const double2 *)pxy_c, t_c, edofs_c, uh_c, out6, bad.p);
+    MWX_LAUNCH_CHECK();
+    int h = 0;
+    MWX_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MWX_CUDA(cudaStreamSynchronize(st));
+    return h ? MWX_E_BADARG : 0;
 }
 
 extern "C" int mwx_assemble_morley_mass(int64_t nrows, int64_t nt, int32_t nq, const double *xw, const double *pxy,

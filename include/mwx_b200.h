@@ -314,6 +314,15 @@ int mwx_morley_error_sums_problem(int32_t problem, int64_t nt, int32_t nq, const
                                   const int32_t *t, const int32_t *edofs, const double *uh, double *sums3,
                                   void *stream);
 
+/* main/example2 (ref main/example2/run.py:101-172): samples (u, ux, uy, uxx, uxy, uyy) of a Morley function of a
+ * coarse mesh at the quadrature points of a mesh refined uniformly from it (coarse triangle of fine triangle T is
+ * T mod nt_c; replaces the per-point ``test_basis['u'].interpolator(test_uh0)(x)`` loops and the DG-P1/DG-P0
+ * ``project(..., diff=)`` chain, which is exact for a piecewise quadratic).  out6 = 6 arrays of nt_f*nq, the
+ * ``exact6`` layout of mwx_morley_error_sums.  MWX_E_BADARG if a point falls outside its assumed triangle. */
+int mwx_morley_sample_nested(int64_t nt_f, int32_t nq, const double *xw, const double *pxy_f, const int32_t *t_f,
+                             int64_t nt_c, const double *pxy_c, const int32_t *t_c, const int32_t *edofs_c,
+                             const double *uh_c, double *out6, void *stream);
+
 /* project(exact_u, basis_to=basis['u']) of example 3 (ref main/example3/run.py:66, main/example3/utils.py:494-565):
  * Morley mass matrix (quadrature, same pattern as K2) and the load vector int f phi_r (f sampled at the points). */
 int mwx_assemble_morley_mass(int64_t nrows, int64_t nt, int32_t nq, const double *xw, const double *pxy,

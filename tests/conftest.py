@@ -27,6 +27,12 @@ def golden_iterations():
 
 
 @pytest.fixture(scope='session')
+def golden_example2():
+    with open(os.path.join(GOLDEN, 'example2_tables.json')) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope='session')
 def cuda():
     import torch
     if not torch.cuda.is_available():

@@ -45,6 +45,21 @@ def norms():
     return out
 
 
+def example2():
+    """main/example2/log/ex3_*_2021-02-06_*.csv: rows 0-5 = levels 1-6 against the level-7 solution (the files were
+    extended by hand below those rows with a transposed copy and a LaTeX table; only the first block is data)."""
+    src = {'P1_pen': 'ex3_P1_pen_2021-02-06_10-55-09.csv', 'P1_nopen': 'ex3_P1_nopen_2021-02-06_10-55-24.csv',
+           'P2_pen': 'ex3_P2_pen_2021-02-06_10-55-13.csv', 'P2_nopen': 'ex3_P2_nopen_2021-02-06_10-55-20.csv'}
+    out = dict(config=dict(example='ex3', base_order=7, refine_time=6, intorder=3, tol=1e-8, epsilon=1e-6, sigma=5,
+                           solver_type='mgcg'), columns=['L2', 'H1', 'H2', 'Energy'], tables={})
+    for key, name in src.items():
+        with open(os.path.join(REF, 'example2/log', name), newline='') as f:
+            rows = list(csv.reader(f))[1:7]
+        assert [r[0] for r in rows] == [str(i) for i in range(6)], key
+        out['tables'][key] = dict(source='main/example2/log/' + name, rows=[[float(v) for v in r[1:5]] for r in rows])
+    return out
+
+
 def iterations():
     rel = 'example1/test/log/test_solver_original_amg1_ex1_8_2020-11-20_12-58-38.txt'
     txt = open(os.path.join(REF, rel)).read().replace('\r', '')
@@ -66,4 +81,6 @@ if __name__ == '__main__':
         json.dump(norms(), f, indent=1)
     with open(os.path.join(OUT, 'amg1_iterations.json'), 'w') as f:
         json.dump(iterations(), f, indent=1)
+    with open(os.path.join(OUT, 'example2_tables.json'), 'w') as f:
+        json.dump(example2(), f, indent=1)
     print('wrote', os.listdir(OUT))
