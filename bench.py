@@ -376,10 +376,14 @@ def run_single(args, torch, F, L, dev, local):
     xstar = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 2 - 1     # manufactured solution
     b = Kc.dot(xstar)
     mls, t_amg = {}, {}
-    for mode in modes:
+
+    def build(mode):                         # one hierarchy at a time lives on the device (40 GB for 'sa' at level 12)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         mls[mode] = F.AMGHierarchy(Kc, mode=mode)
+        torch.cuda.synchronize()
         t_amg[mode] = time.perf_counter() - t0
+    build(args.mode)
     # pinned host inputs / outputs for the end-to-end leg
     p_host = torch.empty(2 * gm.nv, dtype=torch.float64).pin_memory()
     t_host = torch.empty(3 * gm.nt, dtype=torch.int32).pin_memory()
@@ -469,26 +473,14 @@ def run_single(args, torch, F, L, dev, local):
                 'value_incl_amg_setup_mdof_s': N / (ms_step_ * 1e-3 + setup) / 1e6,
                 'pcg_iters': its, 'pcg_info': rr[-1]['info'], 'pcg_s_per_solve': mean('pcg', rr) * 1e-3,
                 'pcg_ms_per_iter': mean('pcg', rr) / max(its, 1),
-                'amg_setup_s': setup, 'amg_host_setup_s': ml.setup_host_seconds, 'amg_upload_s': ml.upload_seconds,
+                'amg_setup_s': setup, 'amg_setup_where': ml.setup, 'amg_host_setup_s': ml.setup_host_seconds,
+                'amg_device_setup_s': ml.setup_device_seconds, 'amg_upload_s': ml.upload_seconds,
                 'amg_reorder_s': ml.reorder_seconds, 'levels': ml.level_sizes(),
                 'operator_complexity': ml.operator_complexity(),
                 'rel_err_vs_manufactured': float(torch.linalg.norm(rr[-1]['x'] - xstar) / torch.linalg.norm(xstar))}
 
     by_mode = {args.mode: mode_block(args.mode, ms_step, e2e_ms / args.steps, rs)}
     x_by_mode = {args.mode: rs[-1]['x']}
-    for mode in modes[1:]:                             # the spec mode beside it: same step function, fewer steps
-        try:
-            k = max(1, min(2, args.steps))
-            tms, rr = timed(False, mode, k, 1)
-            by_mode[mode] = mode_block(mode, tms / k, None, rr)
-            by_mode[mode]['steps'] = k
-            x_by_mode[mode] = rr[-1]['x']
-        except Exception as exc:                        # never let the side measurement take the bench line down
-            by_mode[mode] = {'error': repr(exc)[:300]}
-    if len(x_by_mode) == 2:
-        xa, xb = x_by_mode[modes[0]], x_by_mode[modes[1]]
-        by_mode['rel_diff_between_modes_tol1e-8_manufactured_rhs'] = float(torch.linalg.norm(xa - xb) / torch.linalg.norm(xb))
-    del x_by_mode
 
     # ---------------------------------------------------------------- the real example-1 problem on this level and the two below
     ex1 = None
@@ -506,44 +498,83 @@ def run_single(args, torch, F, L, dev, local):
         except Exception as exc:
             ex1['levels'][str(args.level)] = {'error': repr(exc)[:300]}
 
+    # one hierarchy at a time: release the headline hierarchy, time the reference-shaped call, then the spec mode
+    ml_levels, ml_reordered = mls[args.mode].levels, mls[args.mode].reordering is not None
+    mls.pop(args.mode)
+    torch.cuda.empty_cache()
+    # the reference-shaped call: solver_iter_mgcg(tol)(A, b) rebuilds the hierarchy inside every call
+    # (ref main/example1/utils.py:150-164) - timed end to end, setup included, on the step's own system
+    closure = None
+    try:
+        Kcl, _ = plan.apply(K2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol = F.solver_iter_mgcg(tol=TOL, maxiter=2000, mode=args.mode)
+        xcl, itcl = sol.solve_with_info(Kcl, b)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        closure = {'call': "solver_iter_mgcg(tol=%g, mode=%r)(K2c, b) with K2c and b on the device" % (TOL, args.mode),
+                   's_per_call': dt, 'amg_setup_s': sol.last['setup_seconds'], 'solve_s': sol.last['solve_seconds'],
+                   'iters': itcl, 'info': sol.last['info'], 'mdof_s': N / dt / 1e6,
+                   'rel_err_vs_manufactured': float(torch.linalg.norm(xcl - xstar) / torch.linalg.norm(xstar))}
+        del Kcl, xcl, sol
+    except Exception as exc:
+        closure = {'error': repr(exc)[:300]}
+    torch.cuda.empty_cache()                 # the library allocates with cudaMalloc: hand torch's cached blocks back
+    for mode in modes[1:]:                             # the spec mode beside it: same step function, fewer steps
+        try:
+            build(mode)
+            k = max(1, min(2, args.steps))
+            tms, rr = timed(False, mode, k, 1)
+            by_mode[mode] = mode_block(mode, tms / k, None, rr)
+            by_mode[mode]['steps'] = k
+            x_by_mode[mode] = rr[-1]['x']
+        except Exception as exc:                        # never let the side measurement take the bench line down
+            by_mode[mode] = {'error': repr(exc)[:300]}
+    if len(x_by_mode) == 2:
+        xa, xb = x_by_mode[modes[0]], x_by_mode[modes[1]]
+        by_mode['rel_diff_between_modes_tol1e-8_manufactured_rhs'] = float(torch.linalg.norm(xa - xb) / torch.linalg.norm(xb))
+    del x_by_mode
+
     # free the big level before the side measurements
     same_cfg = None
     asm_renum_ms = None
-    if args.level <= 12:
-        gm2 = gm.renumbered()
-        basis2 = F.InteriorBasis(gm2, F.ElementTriMorley(), intorder=5)
-        K2r = F.asm_gpu(form, basis2)
-        for _ in range(3):
-            F.asm_gpu(form, basis2, out=K2r.d_data)
-        e0, e1 = ev(), ev()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            F.asm_gpu(form, basis2, out=K2r.d_data)
-        e1.record()
-        torch.cuda.synchronize()
-        asm_renum_ms = e0.elapsed_time(e1) / 5
-        del K2r, basis2, gm2
-        torch.cuda.empty_cache()
-
     peak, peak_src = measured_peaks()
     spmv_bytes = 12 * nnzc + 20 * n                            # values 8 + col 4 per nnz; 20 B/row
     asm_bytes = 308 * nt                                       # DESIGN.md section 4 (gather formulation)
     spmv_gbs = spmv_bytes / (mean('spmv', rs) * 1e-3) / 1e9
     asm_gbs = asm_bytes / (mean('asm', rs) * 1e-3) / 1e9
     iters = rs[-1]['its']
-    ml = mls[args.mode]
-    nlev = ml.levels
+    nlev = ml_levels
     per_vcycle = (nlev - 1) * 7 + 1      # per level: first step, 1 smoother SpMV, residual, restrict, prolong, 2 smoother SpMVs; + coarse gemv
     gpu_launches = int(args.steps * (2 + 1 + 1 + 1 + 3 + iters * (4 + per_vcycle)))
     level_main = args.level
-    numbering = 'hilbert (solver-internal)' if ml.reordering is not None else 'skfem'
+    numbering = 'hilbert (solver-internal)' if ml_reordered else 'skfem'
 
     # release the level-L objects, then the smaller side blocks
-    del ml, mls, K2, Kc, plan, basis, pat, gm, vals, vals_c, perm_bufs, ysp, xstar, b, rs_e2e
+    del mls, K2, Kc, plan, basis, pat, gm, vals, vals_c, perm_bufs, ysp, xstar, b, rs_e2e
     for r in rs:
         r.pop('x', None)
     torch.cuda.empty_cache()
+    if args.level <= 12:                                       # same triangles, Hilbert-renumbered mesh (MeshTri.renumbered())
+        try:
+            gm2 = F.MeshTri().refine(args.level).renumbered()
+            basis2 = F.InteriorBasis(gm2, F.ElementTriMorley(), intorder=5)
+            K2r = F.asm_gpu(form, basis2)
+            for _ in range(3):
+                F.asm_gpu(form, basis2, out=K2r.d_data)
+            e0, e1 = ev(), ev()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                F.asm_gpu(form, basis2, out=K2r.d_data)
+            e1.record()
+            torch.cuda.synchronize()
+            asm_renum_ms = e0.elapsed_time(e1) / 5
+            del K2r, basis2, gm2
+        except Exception:
+            asm_renum_ms = None
+        torch.cuda.empty_cache()
     if ex1 is not None:
         for lvl in (args.level - 1, args.level - 2):
             if lvl < 3:
@@ -591,6 +622,7 @@ def run_single(args, torch, F, L, dev, local):
                    'l2': 'operator (9.3 GB) and vectors (0.5 GB each) exceed the 126 MB L2; a 256 MiB buffer is '
                          'written before the SpMV sample'},
         'modes': by_mode,
+        'reference_shaped_call': closure,
         'assembly_mdof_s': N / (mean('asm', rs) * 1e-3) / 1e6,
         'assembly_ms': mean('asm', rs), 'condense_ms': mean('condense', rs),
         'pcg': {'s_per_solve': mean('pcg', rs) * 1e-3, 'iters': iters, 'info': rs[-1]['info'], 'mode': args.mode,

@@ -85,6 +85,12 @@ _SIGNATURES = {
     'mwx_gs_wavefronts_host': [i64, vp, vp, vp, vp, _pi64],
     'mwx_gs_wavefronts_backward_host': [i64, vp, vp, vp, vp, _pi64],
     'mwx_amg_upload': [vp, i32, i32, vp, ctypes.POINTER(vp), vp],
+    'mwx_amg_setup_sa_dev': [i64, vp, vp, vp, vp, i32, i32, i32, f64, i32, i32, i32, i32, ctypes.POINTER(vp), vp],
+    'mwx_amg_dev_finalize': [vp, vp, vp],
+    'mwx_amg_dev_num_levels': [vp],
+    'mwx_amg_dev_level_dims': [vp, i32, i32, vp],
+    'mwx_amg_dev_level_copy': [vp, i32, i32, vp, vp, vp, vp],
+    'mwx_amg_dev_level_aux': [vp, i32, vp, _pi64, _pi32, vp, _pi32, vp],
     'mwx_amg_level_rho': [vp, i32, _pf64],
     'mwx_amg_set_chebyshev': [vp, i32, f64],
     'mwx_amg_destroy_dev': [vp],

@@ -171,7 +171,10 @@ inline unsigned vgrid(int64_t n) {
 
 }  // namespace
 
-void free_csr(DCsr &m) { cudaFree(m.ptr); cudaFree(m.idx); cudaFree(m.val); m = DCsr(); }
+void free_csr(DCsr &m) {
+    if (!m.borrowed) { cudaFree(m.ptr); cudaFree(m.idx); cudaFree(m.val); }
+    m = DCsr();
+}
 
 }  // namespace mwx
 
@@ -193,7 +196,7 @@ extern "C" void mwx_amg_destroy_dev(mwx_amg_dev_t *d) {
     delete d;
 }
 
-static int estimate_rho(mwx_amg_dev *d, DLevel &L, cudaStream_t st) {
+int mwx::amg_estimate_rho(mwx_amg_dev *d, DLevel &L, cudaStream_t st) {
     // power iteration on D^-1 A with a fixed pseudo-random start (deterministic)
     const int64_t n = L.A.rows;
     double *v = L.x2, *w = L.r;               // scratch: both are free outside a cycle
@@ -248,14 +251,14 @@ int mwx::amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_ho
         if (l + 1 < nl) {
             if ((rc = plan(L.P)) || (rc = plan(L.R))) return rc;
             const size_t bytes = sizeof(double) * (size_t)n;
-            if (cudaMalloc((void **)&L.dinv, bytes) != cudaSuccess || cudaMalloc((void **)&L.r, bytes) != cudaSuccess ||
-                cudaMalloc((void **)&L.x2, bytes) != cudaSuccess || cudaMalloc((void **)&L.d, bytes) != cudaSuccess)
-                return MWX_E_NOMEM;
-            if ((rc = launch_csr_diagonal(n, L.A.ptr, L.A.idx, L.A.val, L.dinv, 1, st))) return rc;
+            const bool have_dinv = L.dinv != nullptr;       // a device setup has already needed it
+            auto need = [&](double **p) { return *p || cudaMalloc((void **)p, bytes) == cudaSuccess; };
+            if (!need(&L.dinv) || !need(&L.r) || !need(&L.x2) || !need(&L.d)) return MWX_E_NOMEM;
+            if (!have_dinv && (rc = launch_csr_diagonal(n, L.A.ptr, L.A.idx, L.A.val, L.dinv, 1, st))) return rc;
         }
         if (l > 0) {
             const size_t bytes = sizeof(double) * (size_t)n;
-            if (cudaMalloc((void **)&L.x, bytes) != cudaSuccess || cudaMalloc((void **)&L.b, bytes) != cudaSuccess)
+            if ((!L.x && cudaMalloc((void **)&L.x, bytes) != cudaSuccess) || (!L.b && cudaMalloc((void **)&L.b, bytes) != cudaSuccess))
                 return MWX_E_NOMEM;
         }
     }
@@ -317,7 +320,7 @@ int mwx::amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_ho
             if ((rc = upload(ord, &L.ord_b, st)) || (rc = upload(wp, &L.wp_b, st))) return rc;
             cudaStreamSynchronize(st);
         } else {
-            if ((rc = estimate_rho(d, L, st))) return rc;
+            if (L.rho <= 0.0 && (rc = amg_estimate_rho(d, L, st))) return rc;
         }
     }
     cudaStreamSynchronize(st);

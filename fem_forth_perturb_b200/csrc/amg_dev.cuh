@@ -10,6 +10,7 @@ namespace mwx {
 struct DCsr {
     int64_t rows = 0, cols = 0, nnz = 0;
     int64_t plan = -1;                         // -(planned SpMV tile height), see spmv_plan_rows
+    bool borrowed = false;                     // the arrays belong to the caller (fine-level operator of a device setup)
     int64_t *ptr = nullptr;
     int32_t *idx = nullptr;
     double *val = nullptr;
@@ -49,4 +50,6 @@ struct mwx_amg_dev {
 
 namespace mwx {
 int amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_host, cudaStream_t st);
+// L.rho = spectral radius of D^-1 A by power iteration (needs L.dinv, L.x2, L.r, L.A.plan and d->sc / d->partials).
+int amg_estimate_rho(mwx_amg_dev *d, DLevel &L, cudaStream_t st);
 }

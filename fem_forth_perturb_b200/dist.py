@@ -16,6 +16,7 @@ the tests, under gloo on CPU).  The kernels behind ``CudaOps`` are the same ones
 import ctypes
 import os
 import math
+import time
 
 import numpy as np
 
@@ -688,7 +689,7 @@ class DistAMG:
     Smoother = Chebyshev (fast mode); iteration counts match the single-GPU fast mode to round-off."""
 
     def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=500000,
-                 max_levels=10, ops=None):
+                 max_levels=10, ops=None, setup='device'):
         """mode 'chebyshev': the reference's Ruge-Stueben hierarchy; 'sa': smoothed aggregation (the global matrix
         must carry near-nullspace candidates, see AMGHierarchy).  Chebyshev smoothing either way."""
         torch = L.require_cuda()
@@ -702,12 +703,17 @@ class DistAMG:
         dev = parts[0].vals.device
         world = comm.world
         offsets0 = parts[0].partition.offsets
-        # ---- root: host hierarchy of the global matrix, shipped level by level
+        # ---- global hierarchy.  mode 'sa' (default setup 'device'): EVERY rank builds it on its own GPU with the
+        # deterministic device setup (bit-identical on all ranks, 1-2 s at 67 M DOFs, no broadcast, no idle GPUs).
+        # Ruge-Stueben, or setup='host': the root builds it on its host and ships it level by level.
+        replicated = mode == 'sa' and setup == 'device'
         payload, meta = None, None
-        if comm.is_root():
+        if replicated or comm.is_root():
+            t_h = time.perf_counter()
             host = AMGHierarchy(global_matrix() if callable(global_matrix) else global_matrix, mode=mode,
-                                max_levels=max_levels, reorder=False, upload=False)
+                                max_levels=max_levels, reorder=False, upload=False, setup=('device' if replicated else 'host'))
             self.setup_host_seconds = host.setup_host_seconds
+            self.setup_device_seconds = host.setup_device_seconds
             sizes = host.level_sizes()
             nl = len(sizes)
             lsw = nl - 1
@@ -720,20 +726,20 @@ class DistAMG:
                 offs.append(host.coarse_offsets(l, offs[l]))
             payload = [torch.tensor([nl, lsw] + [o for lv in offs for o in lv], dtype=torch.int64, device=dev)]
 
-            def put(M):
-                payload.extend([torch.from_numpy(M.indptr.astype(np.int64)).to(dev),
-                                torch.from_numpy(M.indices.astype(np.int32)).to(dev),
-                                torch.from_numpy(M.data.astype(np.float64)).to(dev)])
+            def put(l, which):
+                payload.extend(host.level_tensors(l, which))
             for l in range(lsw):
                 if l > 0:
-                    put(host.level_matrix(l, 0))
-                put(host.level_matrix(l, 1))
-                put(host.level_matrix(l, 2))
-            put(host.level_matrix(lsw, 0))
+                    put(l, 0)
+                put(l, 1)
+                put(l, 2)
+            put(lsw, 0)
             if mode == 'sa':                   # the replicated tail continues the aggregation from level lsw
                 payload.append(torch.from_numpy(host.level_candidates(lsw)).to(dev))
             del host
-        payload = comm.broadcast_tensors(payload)
+            self.setup_global_seconds = time.perf_counter() - t_h
+        if not replicated:
+            payload = comm.broadcast_tensors(payload)
         head = payload[0].cpu().numpy()
         nl, lsw = int(head[0]), int(head[1])
         offs = [list(map(int, head[2 + l * (world + 1):2 + (l + 1) * (world + 1)])) for l in range(lsw + 1)]

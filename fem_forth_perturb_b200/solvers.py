@@ -138,20 +138,29 @@ class AMGHierarchy:
     MODES = {'parity': 0, 'chebyshev': 1, 'jacobi': 2, 'sa': 1}
 
     def __init__(self, A, mode='parity', degree=2, theta=None, max_levels=10, max_coarse=None, reorder=None,
-                 upload=True, candidates=None, block_size=1, first_level=0):
+                 upload=True, candidates=None, block_size=1, first_level=0, setup=None):
         """mode 'sa' (throughput, no reference counterpart): smoothed-aggregation hierarchy on the near-nullspace
         candidates of A (``A.candidates`` - attached by ``asm_gpu`` on a Morley basis: the interpolants of 1, x, y -
         or the ``candidates`` argument, (n, k)), Chebyshev smoothing.  The other modes use pyamg's Ruge-Stueben
-        hierarchy (theta 0.25, max_coarse 10)."""
+        hierarchy (theta 0.25, max_coarse 10).
+
+        setup: 'host' = C++/OpenMP setup + upload (the only choice for the Ruge-Stueben modes: its C/F splitting is a
+        serial sweep whose tie-breaks the reference's iteration counts depend on); 'device' = every pass of the
+        smoothed-aggregation setup as CUDA kernels, nothing leaves HBM (default for mode 'sa' when ``upload``)."""
         torch = L.require_cuda()
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {list(self.MODES)}")
         sa = mode == 'sa'
+        if setup is None:
+            setup = 'device' if (sa and upload) else 'host'
+        if setup not in ('host', 'device') or (setup == 'device' and not sa):
+            raise ValueError("setup='device' is the smoothed-aggregation setup (mode='sa')")
         theta = (0.1 if sa else 0.25) if theta is None else theta
         max_coarse = (300 if sa else 10) if max_coarse is None else max_coarse
         lib = L.lib()
         A = _to_device_csr(A)
-        self.n, self.mode = A.shape[0], mode
+        self.n, self.mode, self.setup = A.shape[0], mode, setup
+        self._host, self._dev, self._keep = None, None, None
         # fast modes run on a locality-renumbered copy; parity mode must keep skfem's order (GS depends on it)
         if reorder is None:
             reorder = mode != 'parity'
@@ -165,6 +174,8 @@ class AMGHierarchy:
                                  "basis carry them (also through condense); otherwise pass candidates=(n, k)")
             if isinstance(cand, np.ndarray):
                 cand = torch.from_numpy(np.ascontiguousarray(cand, dtype=np.float64)).to(A.d_data.device)
+            if cand.ndim != 2 or cand.shape[0] != self.n or not 1 <= cand.shape[1] <= 8:
+                raise ValueError("candidates must be an (n, k) array with 1 <= k <= 8")
         t0 = time.perf_counter()
         self.reordering = Reordering.for_matrix(A) if reorder else None
         if self.reordering is not None:
@@ -173,7 +184,28 @@ class AMGHierarchy:
                 cand = cand[self.reordering.perm.long()]
             torch.cuda.synchronize()
         self.reorder_seconds = time.perf_counter() - t0
+        self.upload_seconds = 0.0
         t0 = time.perf_counter()
+        if setup == 'device':
+            ip = A.d_indptr if A.d_indptr.dtype == torch.int64 else A.d_indptr.to(torch.int64)
+            cand = cand.contiguous().to(torch.float64)
+            self._keep = (A, ip)                    # the device hierarchy borrows the fine-level arrays (candidates are copied)
+            self._dev = ctypes.c_void_p()
+            L.check(lib.mwx_amg_setup_sa_dev(self.n, L.ptr(ip), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(cand),
+                                             cand.shape[1], int(block_size), int(first_level), float(theta),
+                                             int(max_levels), int(max_coarse),
+                                             self.MODES[mode], int(degree), ctypes.byref(self._dev), L.stream()),
+                    'mwx_amg_setup_sa_dev')
+            self.levels = lib.mwx_amg_dev_num_levels(self._dev)
+            if upload:                      # upload=False: operators only (the partitioned solver slices them itself)
+                self._check_coarsest()
+                Ac = self.level_matrix(self.levels - 1, 0).toarray()
+                pinv = self._pinv2(Ac)
+                L.check(lib.mwx_amg_dev_finalize(self._dev, L.ptr(pinv), L.stream()), 'mwx_amg_dev_finalize')
+            torch.cuda.synchronize()
+            self.setup_host_seconds = 0.0
+            self.setup_device_seconds = time.perf_counter() - t0
+            return
         ip = np.ascontiguousarray(A.d_indptr.cpu().numpy(), dtype=np.int64)
         ix = np.ascontiguousarray(A.d_indices.cpu().numpy(), dtype=np.int32)
         va = np.ascontiguousarray(A.d_data.cpu().numpy(), dtype=np.float64)
@@ -181,9 +213,7 @@ class AMGHierarchy:
         import os
         lib.mwx_set_host_threads(int(os.environ.get('MWX_HOST_THREADS', os.cpu_count() or 1)))
         if sa:
-            Bh = np.ascontiguousarray(cand.cpu().numpy() if hasattr(cand, 'cpu') else cand, dtype=np.float64)
-            if Bh.ndim != 2 or Bh.shape[0] != self.n or not 1 <= Bh.shape[1] <= 8:
-                raise ValueError("candidates must be an (n, k) array with 1 <= k <= 8")
+            Bh = np.ascontiguousarray(cand.cpu().numpy(), dtype=np.float64)
             L.check(lib.mwx_amg_setup_sa_host(self.n, L.ptr(ip), L.ptr(ix), L.ptr(va), L.ptr(Bh), Bh.shape[1],
                                               int(block_size), int(first_level), float(theta), int(max_levels),
                                               int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_sa_host')
@@ -192,32 +222,41 @@ class AMGHierarchy:
                                            int(max_coarse), ctypes.byref(self._host)), 'mwx_amg_setup_host')
         self.levels = lib.mwx_amg_num_levels(self._host)
         self.setup_host_seconds = time.perf_counter() - t0
-        self._dev = None
-        self.upload_seconds = 0.0
+        self.setup_device_seconds = 0.0
         if not upload:                      # host hierarchy only (the partitioned solver distributes it itself)
             return
         t1 = time.perf_counter()
         # coarsest level: dense pseudo-inverse (scipy 1.4.1 pinv2 semantics) through LAPACK
-        if self.level_dims(self.levels - 1, 0)[0] > 8192:
-            raise RuntimeError(f"AMG coarsening stopped at {self.level_dims(self.levels - 1, 0)[0]} rows (levels "
-                               f"{self.level_sizes()}): too large for the dense coarse solve; raise max_levels or "
-                               f"lower theta")
-        Ac = self.level_matrix(self.levels - 1, 0).toarray()
-        u, s, vh = np.linalg.svd(Ac, full_matrices=False)
-        rank = int(np.sum(s > 1e6 * np.finfo(np.float64).eps * s.max())) if s.size else 0
-        pinv = np.ascontiguousarray(((u[:, :rank] / s[:rank]) @ vh[:rank]).T)
+        self._check_coarsest()
+        pinv = self._pinv2(self.level_matrix(self.levels - 1, 0).toarray())
         self._dev = ctypes.c_void_p()
         L.check(lib.mwx_amg_upload(self._host, self.MODES[mode], int(degree), L.ptr(pinv),
                                    ctypes.byref(self._dev), L.stream()), 'mwx_amg_upload')
         torch.cuda.synchronize()
         self.upload_seconds = time.perf_counter() - t1
 
+    def _check_coarsest(self):
+        if self.level_dims(self.levels - 1, 0)[0] > 8192:
+            raise RuntimeError(f"AMG coarsening stopped at {self.level_dims(self.levels - 1, 0)[0]} rows (levels "
+                               f"{self.level_sizes()}): too large for the dense coarse solve; raise max_levels or "
+                               f"lower theta")
+
+    @staticmethod
+    def _pinv2(Ac):
+        """scipy 1.4.1 ``pinv2`` (pyamg's coarse solver): SVD with the cutoff 1e6 * eps * s_max."""
+        u, s, vh = np.linalg.svd(Ac, full_matrices=False)
+        rank = int(np.sum(s > 1e6 * np.finfo(np.float64).eps * s.max())) if s.size else 0
+        return np.ascontiguousarray(((u[:, :rank] / s[:rank]) @ vh[:rank]).T)
+
     def set_chebyshev(self, degree=2, ratio=10.0):
         L.check(L.lib().mwx_amg_set_chebyshev(self._dev, int(degree), float(ratio)), 'mwx_amg_set_chebyshev')
 
     def level_dims(self, level, which=0):
         dims = np.zeros(3, dtype=np.int64)
-        L.check(L.lib().mwx_amg_level_dims(self._host, level, which, L.ptr(dims)), 'mwx_amg_level_dims')
+        if self._host is None:
+            L.check(L.lib().mwx_amg_dev_level_dims(self._dev, level, which, L.ptr(dims)), 'mwx_amg_dev_level_dims')
+        else:
+            L.check(L.lib().mwx_amg_level_dims(self._host, level, which, L.ptr(dims)), 'mwx_amg_level_dims')
         return tuple(int(v) for v in dims)
 
     def level_matrix(self, level, which=0):
@@ -225,9 +264,29 @@ class AMGHierarchy:
         import scipy.sparse as sp
         rows, cols, nnz = self.level_dims(level, which)
         ip = np.empty(rows + 1, np.int64); ix = np.empty(nnz, np.int32); va = np.empty(nnz, np.float64)
-        L.check(L.lib().mwx_amg_level_copy(self._host, level, which, L.ptr(ip), L.ptr(ix), L.ptr(va)),
-                'mwx_amg_level_copy')
+        if self._host is None:
+            L.check(L.lib().mwx_amg_dev_level_copy(self._dev, level, which, L.ptr(ip), L.ptr(ix), L.ptr(va), L.stream()),
+                    'mwx_amg_dev_level_copy')
+        else:
+            L.check(L.lib().mwx_amg_level_copy(self._host, level, which, L.ptr(ip), L.ptr(ix), L.ptr(va)),
+                    'mwx_amg_level_copy')
         return sp.csr_matrix((va, ix, ip), shape=(rows, cols))
+
+    def level_tensors(self, level, which=0):
+        """(indptr, indices, data) of A_l / P_l / R_l as device tensors (copies)."""
+        torch = L.require_cuda()
+        rows, cols, nnz = self.level_dims(level, which)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if self._host is None:
+            ip = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+            ix = torch.empty(nnz, dtype=torch.int32, device=dev)
+            va = torch.empty(nnz, dtype=torch.float64, device=dev)
+            L.check(L.lib().mwx_amg_dev_level_copy(self._dev, level, which, L.ptr(ip), L.ptr(ix), L.ptr(va), L.stream()),
+                    'mwx_amg_dev_level_copy')
+            return ip, ix, va
+        M = self.level_matrix(level, which)
+        return (torch.from_numpy(M.indptr.astype(np.int64)).to(dev), torch.from_numpy(M.indices.astype(np.int32)).to(dev),
+                torch.from_numpy(M.data.astype(np.float64)).to(dev))
 
     def splitting(self, level):
         rows = self.level_dims(level, 0)[0]
@@ -238,6 +297,13 @@ class AMGHierarchy:
     def level_candidates(self, level):
         """(rows, k) near-nullspace candidates of a smoothed-aggregation level."""
         k = ctypes.c_int32(0)
+        if self._host is None:
+            L.check(L.lib().mwx_amg_dev_level_aux(self._dev, level, None, None, None, None, ctypes.byref(k), L.stream()),
+                    'mwx_amg_dev_level_aux')
+            B = np.empty((self.level_dims(level, 0)[0], k.value), dtype=np.float64)
+            L.check(L.lib().mwx_amg_dev_level_aux(self._dev, level, None, None, None, L.ptr(B), None, L.stream()),
+                    'mwx_amg_dev_level_aux')
+            return B
         L.check(L.lib().mwx_amg_level_candidates(self._host, level, None, ctypes.byref(k)), 'mwx_amg_level_candidates')
         B = np.empty((self.level_dims(level, 0)[0], k.value), dtype=np.float64)
         L.check(L.lib().mwx_amg_level_candidates(self._host, level, L.ptr(B), ctypes.byref(k)), 'mwx_amg_level_candidates')
@@ -247,6 +313,14 @@ class AMGHierarchy:
         """Row-block boundaries of level+1 induced by the boundaries ``offsets`` of ``level``: a coarse DOF goes with
         the fine DOF it comes from (its C point, or the seed of its aggregate), so the blocks stay contiguous."""
         k = ctypes.c_int32(0)
+        if self._host is None:
+            na = ctypes.c_int64(0)
+            L.check(L.lib().mwx_amg_dev_level_aux(self._dev, level, None, ctypes.byref(na), ctypes.byref(k), None, None,
+                                                  L.stream()), 'mwx_amg_dev_level_aux')
+            roots = np.empty(na.value, dtype=np.int64)
+            L.check(L.lib().mwx_amg_dev_level_aux(self._dev, level, L.ptr(roots), None, None, None, None, L.stream()),
+                    'mwx_amg_dev_level_aux')
+            return [int(k.value * np.searchsorted(roots, o, side='left')) for o in offsets]
         L.check(L.lib().mwx_amg_level_roots(self._host, level, None, ctypes.byref(k)), 'mwx_amg_level_roots')
         if k.value == 0:                                   # Ruge-Stueben level
             csum = np.concatenate(([0], np.cumsum(self.splitting(level))))

@@ -258,6 +258,31 @@ typedef struct mwx_amg_dev mwx_amg_dev_t;
  * NULL = computed inside by a symmetric Jacobi eigen-solver with pinv2's cutoff. */
 int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t cheby_degree,
                    const double *coarse_pinv_host, mwx_amg_dev_t **out, void *stream);
+/* Smoothed-aggregation setup ON THE DEVICE (throughput mode; no reference counterpart - the reference's
+ * ``pyamg.ruge_stuben_solver(A)``, ref main/example1/utils.py:154, runs per solve and is what mode 'sa' replaces).
+ * Same scheme and parameters as mwx_amg_setup_sa_host; aggregate roots are a maximal independent set of the squared
+ * strength graph instead of the host's serial greedy sweep, every sparse product is a deterministic hash SpGEMM
+ * (csrc/amg_setup_dev.cu).  All arrays are DEVICE pointers; indptr/indices/values are BORROWED as the fine-level
+ * operator and must outlive the hierarchy.  block_size / first_level as in mwx_amg_setup_sa_host (continuing from
+ * one of the scheme's own coarse levels reproduces the remaining levels bit for bit).  smoother 1 (Chebyshev) or
+ * 2 (Jacobi).  The result needs
+ * mwx_amg_dev_finalize (work vectors, SpMV plans, coarse pseudo-inverse) before mwx_amg_vcycle / mwx_pcg_amg.
+ * MWX_E_CAPACITY: a coarse operator lost its ncand x ncand block structure or a product row exceeds 8192 entries. */
+int mwx_amg_setup_sa_dev(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                         const double *candidates, int32_t ncand, int32_t block_size, int32_t first_level,
+                         double theta, int32_t max_levels, int32_t max_coarse, int32_t smoother,
+                         int32_t cheby_degree, mwx_amg_dev_t **out, void *stream);
+/* coarse_pinv_host as in mwx_amg_upload (NULL = computed inside, coarsest level of at most 4096 rows). */
+int mwx_amg_dev_finalize(mwx_amg_dev_t *d, const double *coarse_pinv_host, void *stream);
+int mwx_amg_dev_num_levels(const mwx_amg_dev_t *d);
+/* which / dims as mwx_amg_level_dims; the copy goes to host OR device buffers (cudaMemcpyDefault). */
+int mwx_amg_dev_level_dims(const mwx_amg_dev_t *d, int32_t level, int32_t which, int64_t *dims_host);
+int mwx_amg_dev_level_copy(const mwx_amg_dev_t *d, int32_t level, int32_t which, int64_t *indptr, int32_t *indices,
+                           double *values, void *stream);
+/* Aggregate roots (ascending first DOF of every aggregate's root node), coarse DOFs per root and the near-nullspace
+ * candidates (rows x ncand) of a device-built level; any output pointer may be NULL; roots/candidates host or device. */
+int mwx_amg_dev_level_aux(const mwx_amg_dev_t *d, int32_t level, int64_t *roots, int64_t *nroots_host,
+                          int32_t *coarse_per_root_host, double *candidates, int32_t *ncand_host, void *stream);
 /* Chebyshev smoother: polynomial degree and eigenvalue interval [1.1 rho / ratio, 1.1 rho] (default 2, 10; tuned on the
  * level-11/12 meshes, profiles/r01_tune_amg.txt). */
 int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ratio);

@@ -507,6 +507,58 @@ def test_smoothed_aggregation_mode(cuda):
     assert ml2.level_sizes() == F.AMGHierarchy(Kc, mode='sa', reorder=False).level_sizes()
 
 
+def test_smoothed_aggregation_device_setup(cuda):
+    """mode='sa' builds its hierarchy on the device by default (csrc/amg_setup_dev.cu).  Checked against sparse algebra
+    on the host: R = P^T exactly, A_c = R A P, the smoothed prolongator reproduces the candidates (P B_c = (I - w D^-1 A) B),
+    aggregates cover every node; the setup is bit-reproducible; the solve matches the host-built hierarchy's."""
+    import fem_forth_perturb_b200 as F
+    gm = F.MeshTri().refine(6)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    K = F.asm_gpu(1e-4 * F.a_load + F.b_load, basis)
+    bf = gm.boundary_facets()
+    D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(K.shape[0])
+    Kc, bc, _, I = F.condense(K, f, D=D)
+    ml = F.AMGHierarchy(Kc, mode='sa')
+    assert ml.setup == 'device' and ml.levels >= 3
+    sizes = ml.level_sizes()
+    assert all(n % 3 == 0 for n in sizes[1:]) and sizes[1] * 4 <= sizes[0]
+    assert 1.0 < ml.operator_complexity() < 2.2
+    for l in range(ml.levels - 1):
+        A, P, R = ml.level_matrix(l, 0), ml.level_matrix(l, 1), ml.level_matrix(l, 2)
+        An = ml.level_matrix(l + 1, 0)
+        assert P.has_sorted_indices and R.has_sorted_indices and An.has_sorted_indices
+        assert abs(R - P.T).max() == 0.0
+        G = (R @ A @ P).tocsr()
+        dead = np.flatnonzero(G.diagonal() == 0.0)                       # vanished candidates get a unit diagonal
+        G = G + sp.csr_matrix((np.ones(dead.size), (dead, dead)), shape=G.shape)
+        assert abs(An - G).max() <= 1e-12 * abs(G).max()
+        B, Bc = ml.level_candidates(l), ml.level_candidates(l + 1)
+        dinv = 1.0 / A.diagonal()
+        # P = (I - w D^-1 A) T and T B_c = B, whatever w is: fit w from one entry, then compare everything
+        lhs, AB = P @ Bc - B, dinv[:, None] * (A @ B)
+        k = np.unravel_index(np.argmax(np.abs(AB)), AB.shape)
+        w = -lhs[k] / AB[k]
+        assert 0.3 < w < 1.4
+        assert np.abs(lhs + w * AB).max() <= 1e-9 * max(1.0, np.abs(B).max())
+        assert np.all(np.diff(P.indptr) % 3 == 0) and np.diff(P.indptr).min() >= 3      # every row belongs to an aggregate
+    ml_again = F.AMGHierarchy(Kc, mode='sa')
+    for l in range(ml.levels):
+        a, b = ml.level_matrix(l, 0), ml_again.level_matrix(l, 0)
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+    x_d = pl.direct_solver(Kc.tocsr(), bc)
+    its = {}
+    for setup in ('device', 'host'):
+        mls = F.AMGHierarchy(Kc, mode='sa', setup=setup)
+        x, it, info, _ = F.pcg(Kc, bc, tol=1e-10, amg=mls)
+        assert info == 0 and np.linalg.norm(x.cpu().numpy() - x_d) <= 1e-8 * np.linalg.norm(x_d)
+        its[setup] = it
+    assert its['device'] <= 1.3 * its['host'] + 2, its
+    with pytest.raises(ValueError):
+        F.AMGHierarchy(Kc, mode='chebyshev', setup='device')
+
+
 def test_locality_reordering_is_a_similarity_transform(cuda):
     """Fast-mode solvers run on P A P^T (Hilbert order of the DOF locations) and permute back."""
     import fem_forth_perturb_b200 as F
