@@ -818,7 +818,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
         marks = [ev() for _ in range(5)]
         if e2e:
             gm.d_pxy.copy_(p_host, non_blocking=True)
-            gm.d_t.copy_(t_host, non_blocking=True)
+            if p.tile_plan is None:                   # the tiled kernel reads the connectivity from its plan, not from t
+                gm.d_t.copy_(t_host, non_blocking=True)
             bd = b_host.to(dev, non_blocking=True)
         else:
             bd = b
@@ -877,7 +878,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     line = {
         'metric': 'hot_path_MDOF_per_s', 'value': value, 'unit': 'MDOF/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'value_mode': amg_mode,
+        'value_incl_amg_setup': N / (ms_step * 1e-3 + t_amg) / 1e6,
         'config': {'workload': f'MWX assemble+SpMV+AMG-PCG, unit square level {args.level}: {N} Morley DOFs, {nt} triangles, '
                                f'condensed n={n_glob}, RCB-partitioned into {world} row blocks (Hilbert order inside a block); '
                                f'eps={EPS}, tol={TOL}, rhs=K2c@x*; preconditioner = global ' + ('smoothed-aggregation' if amg_mode == 'sa' else 'RS-AMG') + ' hierarchy applied as a '
@@ -893,12 +895,14 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
         'spmv': {'ms': float(phmax[1]), 'gbs_per_gpu': spmv_gbs_rank, 'frac_of_peak': spmv_gbs_rank / peak,
                  'note': 'local block of the slowest rank, halo not included'},
         'partition': {'rows_max': int(nloc_max), 'ghosts_max': int(phmax[5]), 'nnz_total': int(nnzc_glob)},
-        'setup_s': {'mesh_refine_pattern': t_mesh, 'partition_plan': t_part, 'amg_global_setup_and_distribution': t_amg},
+        'setup_s': {'mesh_refine_pattern': t_mesh, 'partition_plan': t_part, 'amg_global_setup_and_distribution': t_amg,
+                    'amg_setup_where': ('every rank builds the global hierarchy on its own GPU (device setup, bit-identical)' if amg_mode == 'sa' else 'root host, broadcast'),
+                    'amg_device_setup_s': getattr(ml, 'setup_device_seconds', None)},
         'roofline': {'kernel': 'k_spmv (local row block, solver numbering)', 'bound': 'hbm', 'achieved': spmv_gbs_rank,
                      'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs_rank / peak, 'traffic': None, 'peak_source': peak_src,
                      'algorithmic_bytes': spmv_bytes_rank},
         'e2e': {'value': N / (e2e_ms / args.steps * 1e-3) / 1e6, 'unit': 'MDOF/s',
-                'h2d_bytes_per_step': int((p_host.numel() * 8 + t_host.numel() * 4) * world + n_glob * 8),
+                'h2d_bytes_per_step': int((p_host.numel() * 8 + (t_host.numel() * 4 if p.tile_plan is None else 0)) * world + n_glob * 8),
                 'd2h_bytes_per_step': int(n_glob * 8), 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(args.steps * world * (2 + 1 + iters * (4 + per_vcycle))),
         'clocks': clocks,

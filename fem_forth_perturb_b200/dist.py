@@ -155,8 +155,20 @@ class RankSystem(HaloPlan):
         self.cols = torch.empty(self.nnz, dtype=torch.int32, device=dev)
         L.check(lib.mwx_dist_localize(self.nnz, L.ptr(cols_g), self.lo, self.hi, L.ptr(self.ghosts), self.nghost,
                                       self.nloc, L.ptr(self.cols), st), 'mwx_dist_localize')
-        self.raw_vals = torch.empty(self.raw_nnz, dtype=torch.float64, device=dev)
         self.vals = torch.empty(self.nnz, dtype=torch.float64, device=dev)
+        # Hot path A on this rank's rows: the tiled element-once kernel writing STRAIGHT into the local layout (the
+        # plan matches an element's columns against the skfem DOF of every kept entry; Dirichlet columns have no
+        # destination and are skipped).  The row-gather kernel + value gather stays as the fallback for meshes the
+        # plan refuses (MWX_E_CAPACITY) and under MWX_ASM_KERNEL=rows.
+        self.tile_plan, self.raw_vals = None, None
+        if os.environ.get('MWX_ASM_KERNEL', 'tiles') == 'tiles' and self.nloc > 0:
+            from .assembly import TilePlan
+            dst_col = I_dev[partition.perm[cols_g.long()].long()].to(torch.int32).contiguous()
+            dst_len = (self.indptr[1:] - self.indptr[:-1]).to(torch.int32).contiguous()
+            plan = TilePlan(basis, self.rows, self.indptr[:-1].contiguous(), dst_len, dst_col)
+            self.tile_plan = plan if plan.ok else None
+        if self.tile_plan is None:
+            self.raw_vals = torch.empty(self.raw_nnz, dtype=torch.float64, device=dev)
         rows_plan = ctypes.c_int32(0)
         L.check(lib.mwx_spmv_plan(self.nloc, L.ptr(self.indptr), ctypes.byref(rows_plan), st), 'mwx_spmv_plan')
         self.spmv_hint = -int(rows_plan.value)
@@ -168,6 +180,9 @@ class RankSystem(HaloPlan):
         from .forms import as_form
         f = as_form(form)
         m, pat, lib, st = self.basis.mesh, self.basis.pattern(), L.lib(), L.stream()
+        if self.tile_plan is not None:
+            self.tile_plan.assemble(m, f.terms.get('a_load', 0.0), f.terms.get('b_load', 0.0), self.vals)
+            return self
         L.check(lib.mwx_assemble_morley_rows(self.nloc, L.ptr(self.rows), L.ptr(self.raw_indptr), m.nt, L.ptr(m.d_pxy),
                                              L.ptr(m.d_t), L.ptr(pat['exy']), 1, L.ptr(pat['r2e_ptr']), L.ptr(pat['r2e_idx']),
                                              L.ptr(pat['slot8']), L.ptr(pat['indptr']), f.terms.get('a_load', 0.0),
@@ -539,13 +554,13 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
     if not same:
         if cache is not None and hasattr(cache['key'][0], 'release'):
             for st in cache['S']:
-                cache['key'][0].release([st['x'], st['p']])
+                cache['key'][0].release([st['x'], st['p'], st['xp']])
         S = []
         for p, b in zip(parts, b_list):
             dev = b.device
             S.append(dict(b=ops.zeros(p.nloc, dev), ws=ops.workspace(dev), x=comm.ext_zeros(p, dev),
-                          p=comm.ext_zeros(p, dev), r=ops.zeros(p.nloc, dev), q=ops.zeros(p.nloc, dev), z=None,
-                          dinv=None))
+                          p=comm.ext_zeros(p, dev), xp=comm.ext_zeros(p, dev), r=ops.zeros(p.nloc, dev),
+                          q=ops.zeros(p.nloc, dev), z=None, dinv=None))
         cache = dict(key=key, S=S)
         parts[0]._cg_state = cache
     S = cache['S']
@@ -613,23 +628,68 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
 
     # (A CUDA-graph replay of `iteration` was tried: capture works, but replayed symmetric-memory barriers mixed
     #  with eager ones deadlock, and a per-solve capture costs more than the ~0.5 ms of launches it saves.)
-    for it in range(1, maxiter + 1):
-        iteration(it == 1)
-        red = [S[0]['ws'][SLOT_RR]]
-        resid = math.sqrt(float(red[-1]))
-        if resid != resid:
-            return xs(), it, it, resid
-        if resid <= atol:
-            if it == 1:
-                return xs(), it, 0, resid
-            comm.halo(parts, [st['x'] for st in S])              # true-residual re-check (scipy 1.4.1)
-            for p, st in zip(parts, S):
-                ops.residual(p, st['x'], st['b'], st['r'], st['dinv'], st['ws'])
+    #
+    # The stopping test lags ONE iteration behind the launches: ||r_k|| travels to pinned host memory behind
+    # iteration k while the host is already queueing iteration k + 1, so the device never waits for the ~100 ctypes
+    # launches of an iteration (the blocking read-back used to expose them on every iteration - at 8 GPUs a third
+    # of the iteration time).  The iterate of iteration k is kept in `xp` (one device copy per iteration), so the
+    # returned x, the iteration count and the true-residual re-check are exactly those of the unlagged loop.
+    import torch
+    on_gpu = S[0]['ws'].is_cuda
+    rr_host = [torch.empty(1, dtype=torch.float64, pin_memory=on_gpu) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)] if on_gpu else None
+    xs_prev = lambda: [st['xp'][:p.nloc].clone() for p, st in zip(parts, S)]
+
+    def post(k):                              # ||r_k||^2 -> host, asynchronously
+        rr_host[k & 1].copy_(S[0]['ws'][SLOT_RR:SLOT_RR + 1], non_blocking=True)
+        if on_gpu:
+            ready[k & 1].record()
+
+    def verdict(k, x_vecs, x_out):
+        """Stopping rule of iteration k (whose iterate is x_vecs): None = go on, else the return tuple."""
+        if on_gpu:
+            ready[k & 1].synchronize()
+        resid_k = math.sqrt(float(rr_host[k & 1][0])) if rr_host[k & 1][0] >= 0 else float('nan')
+        if resid_k != resid_k:
+            return x_out(), k, k, resid_k
+        if resid_k <= atol:
+            if k == 1:
+                return x_out(), k, 0, resid_k
+            saved = [st['ws'][:5].clone() for st in S]           # the scalars of the iteration already in flight
+            comm.halo(parts, x_vecs)                             # true-residual re-check (scipy 1.4.1)
+            for p, st, xv in zip(parts, S, x_vecs):
+                ops.residual(p, xv, st['b'], st['q'], st['dinv'], st['ws'])      # q is free between iterations
             red = reduce_slots([SLOT_RHO, SLOT_RR] if jacobi else [SLOT_RR])
-            resid = math.sqrt(float(red[-1]))
-            if resid <= atol:
-                return xs(), it, 0, resid
-    return xs(), maxiter, maxiter, resid
+            true_resid = math.sqrt(float(red[-1]))
+            if true_resid <= atol:
+                return x_out(), k, 0, true_resid
+            # Failed re-check (recurrence and true residual have drifted apart: fp64 floor).  scipy restarts from
+            # the true residual here; the lagged loop keeps the recurrence of the iteration already queued and only
+            # puts its scalars back - the one place where this driver is not scipy 1.4.1 step for step.
+            for st, sv in zip(S, saved):
+                st['ws'][:5].copy_(sv)
+            verdict.last = true_resid
+        else:
+            verdict.last = resid_k
+        return None
+    verdict.last = resid
+
+    for it in range(1, maxiter + 1):
+        if it > 1:
+            for p, st in zip(parts, S):
+                st['xp'][:p.nloc].copy_(st['x'][:p.nloc])        # iterate of iteration it - 1
+        iteration(it == 1)
+        post(it)
+        if it > 1:
+            # NOTE: the re-check's residual kernel and all-reduce run AFTER iteration `it` was queued; they only
+            # read xp / b and write q and the scalar slots, which iteration it + 1 recomputes before using them.
+            out = verdict(it - 1, [st['xp'] for st in S], xs_prev)
+            if out is not None:
+                return out
+    out = verdict(maxiter, [st['x'] for st in S], xs)
+    if out is not None:
+        return out
+    return xs(), maxiter, maxiter, verdict.last
 
 
 class PartitionedProblem:
