@@ -96,6 +96,8 @@ _SIGNATURES = {
     'mwx_amg_destroy_dev': [vp],
     'mwx_amg_vcycle': [vp, vp, vp, vp],
     'mwx_pcg_amg_monitored': [vp, i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, _pi64, vp],
+    'mwx_pcg_amg_history': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp, i64, vp],
+    'mwx_pcg_jacobi_history': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp, i64, vp],
     'mwx_pcg_amg': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp],
 }
 _VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev', 'mwx_asm_plan_destroy'}

@@ -14,6 +14,8 @@
 //   1  fast mode   : Chebyshev polynomial of D^-1 A (degree cheby_degree) - embarrassingly parallel,
 //      symmetric, every step is one fused SpMV-epilogue kernel.
 //   2  fast mode   : two damped-Jacobi steps (omega = 4 / (3 rho)).
+#include <cooperative_groups.h>
+
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -24,26 +26,122 @@
 namespace mwx {
 namespace {
 
-__global__ void __launch_bounds__(1024) k_gs_wavefront_sweep(int64_t nwaves, const int64_t *__restrict__ wave_ptr,
-                                                             const int32_t *__restrict__ order,
-                                                             const int64_t *__restrict__ Ap,
-                                                             const int32_t *__restrict__ Aj,
-                                                             const double *__restrict__ Ax, double *x,
-                                                             const double *__restrict__ b) {
-    for (int64_t w = 0; w < nwaves; ++w) {
-        const int64_t s = wave_ptr[w], e = wave_ptr[w + 1];
-        for (int64_t q = s + threadIdx.x; q < e; q += blockDim.x) {
-            const int32_t i = order[q];
-            double rsum = 0.0, diag = 0.0;
-            for (int64_t k = Ap[i]; k < Ap[i + 1]; ++k) {
-                const int32_t j = Aj[k];
-                if (j == i) diag = Ax[k];
-                else rsum += Ax[k] * x[j];          // plain (coherent) loads: x changes between wavefronts
-            }
-            if (diag != 0.0) x[i] = (b[i] - rsum) / diag;
-        }
-        __syncthreads();
+// Exact lexicographic Gauss-Seidel, level-scheduled (GsSweep in amg_dev.cuh).  A wavefront = rows whose lower-numbered
+// (forward sweep) neighbours are all done; its rows are independent, wavefronts run in order.  Each row is summed by one
+// thread in CSR order with the diagonal skipped - the same sequence of FMAs as a sequential sweep, whatever the launch
+// shape.  Before the barrier that ends a wavefront every thread prefetches the records and entries it will read in
+// the next one (they do not depend on x), so after the barrier only the x gathers are exposed latency.
+__device__ __forceinline__ void gs_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// One row: rsum = sum of a_ij x_j over the off-diagonal entries IN CSR ORDER (one FMA chain - the arithmetic of a
+// sequential sweep), the x gathers issued eight at a time so that their latencies overlap.
+template <bool COHERENT_L1>
+__device__ __forceinline__ void gs_row(const GsRow r, double diag, double bi, const int32_t *__restrict__ col,
+                                       const double *__restrict__ val, double *x) {
+    const int32_t *__restrict__ c = col + r.start;
+    const double *__restrict__ v = val + r.start;
+    double rsum = 0.0;
+    for (int k = 0; k < r.len; k += 8) {
+        int32_t cc[8];
+        double vv[8], xx[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k + u < r.len) { cc[u] = c[k + u]; vv[u] = v[k + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k + u < r.len) xx[u] = COHERENT_L1 ? x[cc[u]] : __ldcg(x + cc[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k + u < r.len) rsum += vv[u] * xx[u];
     }
+    if (diag != 0.0) x[r.row] = (bi - rsum) / diag;
+}
+
+// The sweep, shared by the two launch shapes.  Everything a thread needs for its first row of the NEXT wavefront that
+// does not depend on x (row record, diagonal, right-hand side, the wavefront bounds; its entries are prefetched into
+// L1) is fetched BEFORE the barrier that ends the current wavefront, so after the barrier only the x gathers are
+// exposed latency.  SYNC() = block barrier (one CTA) or cooperative grid barrier.
+template <bool COHERENT_L1, typename Sync>
+__device__ __forceinline__ void gs_sweep(const GsSweep &g, double *x, const double *__restrict__ b, int64_t tid,
+                                         int64_t nthreads, Sync sync) {
+    if (g.nwaves <= 0) return;
+    int64_t s = g.wave_ptr[0], e = g.wave_ptr[1];
+    int64_t e_next = g.nwaves > 1 ? g.wave_ptr[2] : e;
+    GsRow r = {0, 0, 0};
+    double dg = 0.0, bi = 0.0;
+    bool have = s + tid < e;
+    if (have) { r = g.rows[s + tid]; dg = g.diag[s + tid]; bi = b[r.row]; }
+    for (int64_t w = 0; w < g.nwaves; ++w) {
+        if (have) gs_row<COHERENT_L1>(r, dg, bi, g.col, g.val, x);
+        for (int64_t q = s + tid + nthreads; q < e; q += nthreads) {          // wavefront wider than the launch
+            const GsRow r2 = g.rows[q];
+            gs_row<COHERENT_L1>(r2, g.diag[q], b[r2.row], g.col, g.val, x);
+        }
+        const int64_t e_after = w + 3 <= g.nwaves ? g.wave_ptr[w + 3] : e_next;
+        have = w + 1 < g.nwaves && e + tid < e_next;
+        if (have) {
+            r = g.rows[e + tid]; dg = g.diag[e + tid]; bi = b[r.row];
+            gs_prefetch(g.col + r.start);
+            gs_prefetch(g.val + r.start);
+            gs_prefetch(g.val + r.start + 15);
+        }
+        sync();
+        s = e; e = e_next; e_next = e_after;
+    }
+}
+
+// One CTA: wavefronts narrower than a few CTAs (coarse levels; a block barrier costs less than a grid barrier).
+__global__ void __launch_bounds__(512) k_gs_wavefront_sweep(GsSweep g, double *x, const double *__restrict__ b) {
+    gs_sweep<true>(g, x, b, threadIdx.x, blockDim.x, [] { __syncthreads(); });      // one SM: its L1 sees its own stores
+}
+
+// Small levels (up to 25 600 rows): the whole symmetric sweep - forward, then backward - in one launch with the iterate
+// held in shared memory, so that the x gathers between two barriers cost a shared-memory access instead of an L2 round
+// trip (a coarse level is a chain of 20-40 narrow wavefronts: pure latency).
+constexpr int64_t GS_SMEM_ROWS = 25600;
+__global__ void __launch_bounds__(512) k_gs_symmetric_sweep_smem(GsSweep gf, GsSweep gb, double *x, const double *__restrict__ b,
+                                                                 int x_is_zero) {
+    extern __shared__ double xs[];
+    const int64_t n = gf.nrows;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) xs[i] = x_is_zero ? 0.0 : x[i];
+    __syncthreads();
+    gs_sweep<true>(gf, xs, b, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+    gs_sweep<true>(gb, xs, b, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) x[i] = xs[i];
+}
+
+// Cooperative grid: wide wavefronts (skfem numbers the DOFs refinement level by refinement level, so the dependency
+// DAG of a 261 k-row Morley operator is only 12 wavefronts deep, ~20 000 rows each).  x is read with ld.global.cg:
+// values written by other SMs in the previous wavefront must not come from a stale L1 line.
+__global__ void __launch_bounds__(256) k_gs_wavefront_sweep_grid(GsSweep g, double *x, const double *__restrict__ b) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    gs_sweep<false>(g, x, b, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
+                    [&] { grid.sync(); });
+}
+
+int launch_gs_sweep(const GsSweep &g, double *x, const double *b, cudaStream_t st) {
+    static int max_blocks = -1;                    // co-resident CTAs of the cooperative kernel on this device
+    if (max_blocks < 0) {
+        int per_sm = 0, coop = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gs_wavefront_sweep_grid, 256, 0) == cudaSuccess)
+            max_blocks = per_sm * sm_count();
+        else
+            max_blocks = 0;
+    }
+    const int64_t avg_wave = g.nwaves > 0 ? g.nrows / g.nwaves : 0;
+    if (max_blocks <= 0 || avg_wave < 768) {            // narrow wavefronts: one CTA, block barriers
+        k_gs_wavefront_sweep<<<1, 512, 0, st>>>(g, x, b);
+        MWX_LAUNCH_CHECK();
+        return 0;
+    }
+    int64_t blocks = (2 * avg_wave + 255) / 256;   // enough threads for a wavefront of twice the average width
+    if (blocks > max_blocks) blocks = max_blocks;
+    GsSweep gg = g;
+    void *args[] = {&gg, &x, &b};
+    MWX_CUDA(cudaLaunchCooperativeKernel((const void *)k_gs_wavefront_sweep_grid, dim3((unsigned)blocks), dim3(256), args, 0, st));
+    return 0;
 }
 
 __global__ void k_dense_gemv(int64_t n, const double *__restrict__ M, const double *__restrict__ v,
@@ -189,7 +287,9 @@ extern "C" void mwx_amg_destroy_dev(mwx_amg_dev_t *d) {
     for (auto &L : d->lv) {
         free_csr(L.A); free_csr(L.P); free_csr(L.R);
         cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.x2); cudaFree(L.b); cudaFree(L.r); cudaFree(L.d);
-        cudaFree(L.ord_f); cudaFree(L.ord_b); cudaFree(L.wp_f); cudaFree(L.wp_b);
+        for (GsSweep *g : {&L.gs_f, &L.gs_b}) {
+            cudaFree(g->wave_ptr); cudaFree(g->rows); cudaFree(g->col); cudaFree(g->val); cudaFree(g->diag);
+        }
         cudaFree(L.roots); cudaFree(L.cand);
     }
     cudaFree(d->pinv); cudaFree(d->sc); cudaFree(d->partials);
@@ -307,18 +407,35 @@ int mwx::amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_ho
             if ((rc = download(L.A, ptr, idx, val))) return rc;
             std::vector<int32_t> ord((size_t)n);
             std::vector<int64_t> wp((size_t)n + 1);
-            int64_t nw = 0;
-            mwx_gs_wavefronts_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
-            wp.resize((size_t)nw + 1);
-            L.nw_f = nw;
-            if ((rc = upload(ord, &L.ord_f, st)) || (rc = upload(wp, &L.wp_f, st))) return rc;
-            cudaStreamSynchronize(st);
-            wp.assign((size_t)n + 1, 0);
-            mwx_gs_wavefronts_backward_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
-            wp.resize((size_t)nw + 1);
-            L.nw_b = nw;
-            if ((rc = upload(ord, &L.ord_b, st)) || (rc = upload(wp, &L.wp_b, st))) return rc;
-            cudaStreamSynchronize(st);
+            for (int backward = 0; backward < 2; ++backward) {
+                int64_t nw = 0;
+                wp.assign((size_t)n + 1, 0);
+                if (backward) mwx_gs_wavefronts_backward_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
+                else mwx_gs_wavefronts_host(n, ptr.data(), idx.data(), ord.data(), wp.data(), &nw);
+                wp.resize((size_t)nw + 1);
+                // pack the operator in wavefront order: one record per row, off-diagonal entries end to end
+                std::vector<GsRow> rows((size_t)n);
+                std::vector<int32_t> col;
+                std::vector<double> vals, diag((size_t)n, 0.0);
+                col.reserve(idx.size()); vals.reserve(val.size());
+                for (int64_t q = 0; q < n; ++q) {
+                    const int32_t i = ord[(size_t)q];
+                    GsRow r;
+                    r.row = i; r.start = (int64_t)col.size();
+                    for (int64_t k = ptr[(size_t)i]; k < ptr[(size_t)i + 1]; ++k) {
+                        if (idx[(size_t)k] == i) diag[(size_t)q] = val[(size_t)k];       // pyamg: the last stored diagonal entry
+                        else { col.push_back(idx[(size_t)k]); vals.push_back(val[(size_t)k]); }
+                    }
+                    r.len = (int32_t)((int64_t)col.size() - r.start);
+                    rows[(size_t)q] = r;
+                }
+                GsSweep &g = backward ? L.gs_b : L.gs_f;
+                g.nwaves = nw; g.nrows = n;
+                if ((rc = upload(wp, &g.wave_ptr, st)) || (rc = upload(rows, &g.rows, st)) || (rc = upload(col, &g.col, st)) ||
+                    (rc = upload(vals, &g.val, st)) || (rc = upload(diag, &g.diag, st)))
+                    return rc;
+                cudaStreamSynchronize(st);
+            }
         } else {
             if (L.rho <= 0.0 && (rc = amg_estimate_rho(d, L, st))) return rc;
         }
@@ -360,12 +477,21 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
     const int64_t n = L.A.rows;
     *xp = x;
     if (d->smoother == 0) {
+        if (n <= GS_SMEM_ROWS && L.gs_f.nwaves > 0 && n / L.gs_f.nwaves < 768) {
+            static bool configured = false;
+            if (!configured) {
+                MWX_CUDA(cudaFuncSetAttribute(k_gs_symmetric_sweep_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(GS_SMEM_ROWS * sizeof(double))));
+                configured = true;
+            }
+            k_gs_symmetric_sweep_smem<<<1, 512, sizeof(double) * (size_t)n, st>>>(L.gs_f, L.gs_b, x, b, x_is_zero ? 1 : 0);
+            MWX_LAUNCH_CHECK();
+            return 0;
+        }
         if (x_is_zero) MWX_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
-        k_gs_wavefront_sweep<<<1, 1024, 0, st>>>(L.nw_f, L.wp_f, L.ord_f, L.A.ptr, L.A.idx, L.A.val, x, b);
-        MWX_LAUNCH_CHECK();
-        k_gs_wavefront_sweep<<<1, 1024, 0, st>>>(L.nw_b, L.wp_b, L.ord_b, L.A.ptr, L.A.idx, L.A.val, x, b);
-        MWX_LAUNCH_CHECK();
-        return 0;
+        int rc;
+        if ((rc = launch_gs_sweep(L.gs_f, x, b, st))) return rc;
+        return launch_gs_sweep(L.gs_b, x, b, st);
     }
     double *cur = x, *alt = L.x2;
     int rc;
@@ -480,6 +606,19 @@ extern "C" int mwx_pcg_amg_monitored(mwx_amg_dev_t *d, int64_t n, const int64_t 
     double *r = work, *z = work + n, *p = work + 2 * n, *q = work + 3 * n;
     return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, nullptr, amg_precond, d, r, z, p, q,
                     iters_host, info_host, resid_host, as_stream(stream), max_rechecks, first_hit_host);
+}
+
+extern "C" int mwx_pcg_amg_history(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_t *indices,
+                                   const double *values, const double *b, double *x, double tol, int64_t maxiter,
+                                   double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
+                                   double *xnorm_hist_host, int64_t xnorm_cap, void *stream) {
+    if (!d || n <= 0 || !indptr || !indices || !values || !b || !x || !work || !iters_host || !info_host || !resid_host ||
+        !xnorm_hist_host || xnorm_cap < 0)
+        return MWX_E_BADARG;
+    if (d->lv[0].A.rows != n) return MWX_E_BADARG;
+    double *r = work, *z = work + n, *p = work + 2 * n, *q = work + 3 * n;
+    return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, nullptr, amg_precond, d, r, z, p, q,
+                    iters_host, info_host, resid_host, as_stream(stream), 0, nullptr, xnorm_hist_host, xnorm_cap);
 }
 
 extern "C" int mwx_smoother_first(int64_t n, const double *b, const double *dinv, double c2, double *x, double *d,

@@ -16,12 +16,24 @@ struct DCsr {
     double *val = nullptr;
 };
 
+// One direction of the exact lexicographic Gauss-Seidel sweep, level-scheduled: rows grouped by dependency wavefront,
+// and for every row, in that order, one 16-byte record plus its off-diagonal entries (CSR order) laid end to end - a
+// wavefront is three contiguous streams, so the next wavefront can be prefetched while the current one computes.
+struct GsRow { int32_t row, len; int64_t start; };
+struct GsSweep {
+    int64_t nwaves = 0, nrows = 0;
+    int64_t *wave_ptr = nullptr;        // (nwaves + 1) offsets into rows[]
+    GsRow *rows = nullptr;              // row id, number of off-diagonal entries, offset of the first one
+    int32_t *col = nullptr;
+    double *val = nullptr;
+    double *diag = nullptr;             // per row, wavefront order
+};
+
 struct DLevel {
     DCsr A, P, R;
     double *dinv = nullptr, *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
-    int32_t *ord_f = nullptr, *ord_b = nullptr;
-    int64_t *wp_f = nullptr, *wp_b = nullptr;
-    int64_t nw_f = 0, nw_b = 0;
+    // parity mode: the operator packed in Gauss-Seidel wavefront order, once per sweep direction (see GsSweep)
+    GsSweep gs_f, gs_b;
     double rho = 0.0;                   // estimate of the spectral radius of D^-1 A
     // smoothed-aggregation levels built on the device keep what the partitioned solver asks for
     int64_t *roots = nullptr;           // first fine DOF of every aggregate (ascending)

@@ -481,7 +481,7 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
              const double *b, double *x, double tol, int64_t maxiter, const double *dinv,
              PrecondFn precond, void *ctx, double *r, double *z, double *p, double *q,
              int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st, int max_rechecks,
-             int64_t *first_hit_host) {
+             int64_t *first_hit_host, double *xnorm_hist_host, int64_t xnorm_cap) {
     Scratch<CgScalars> sc(st);
     int rechecks = 0;
     int64_t floor_it = 0;
@@ -529,8 +529,14 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
         if (rc) return rc;
         k_xr_update<<<vec_grid(n), VEC_THREADS, 0, st>>>(n, p, q, x, r, dinv, sc.p, partials.p, jacobi ? 1 : 0);
         MWX_LAUNCH_CHECK();
-        MWX_CUDA(cudaMemcpyAsync(h, &sc.p->rr, sizeof(double), cudaMemcpyDeviceToHost, st));
+        const bool want_xnorm = xnorm_hist_host && it <= xnorm_cap;
+        if (want_xnorm) {                                        // rr and aux are adjacent: one 16-byte read-back
+            rc = launch_dot(n, x, x, &sc.p->aux, partials.p, &sc.p->ticket[0], st);
+            if (rc) return rc;
+        }
+        MWX_CUDA(cudaMemcpyAsync(h, &sc.p->rr, sizeof(double) * (want_xnorm ? 2 : 1), cudaMemcpyDeviceToHost, st));
         MWX_CUDA(cudaStreamSynchronize(st));
+        if (want_xnorm) xnorm_hist_host[it - 1] = sqrt(h[1]);
         double rn = sqrt(h[0]);
         *iters_host = it; *resid_host = rn;
         if (!(rn == rn)) { *info_host = (int32_t)(it < 0x7fffffff ? it : 0x7fffffff); return MWX_E_NOCONV; }
@@ -628,6 +634,24 @@ extern "C" int mwx_pcg_jacobi(int64_t n, const int64_t *indptr, const int32_t *i
     }
     return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, precondition ? dinv : nullptr,
                     nullptr, nullptr, r, nullptr, p, q, iters_host, info_host, resid_host, st, 0, nullptr);
+}
+
+extern "C" int mwx_pcg_jacobi_history(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                                      const double *b, double *x, double tol, int64_t maxiter, int32_t precondition,
+                                      double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
+                                      double *xnorm_hist_host, int64_t xnorm_cap, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !b || !x || !work || !iters_host || !info_host || !resid_host ||
+        !xnorm_hist_host || xnorm_cap < 0)
+        return MWX_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    double *r = work, *p = work + n, *q = work + 2 * n, *dinv = work + 3 * n;
+    if (precondition) {
+        k_csr_diagonal<<<grid_for(n, 256), 256, 0, st>>>(n, indptr, indices, values, dinv, 1);
+        MWX_LAUNCH_CHECK();
+    }
+    return cg_solve(n, indptr, indices, values, b, x, tol, maxiter, precondition ? dinv : nullptr,
+                    nullptr, nullptr, r, nullptr, p, q, iters_host, info_host, resid_host, st, 0, nullptr,
+                    xnorm_hist_host, xnorm_cap);
 }
 
 // ------------------------------------------------------------------ building blocks for the partitioned CG

@@ -56,6 +56,8 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
              const double *b, double *x, double tol, int64_t maxiter, const double *dinv,
              PrecondFn precond, void *ctx, double *r, double *z, double *p, double *q,
              int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st, int max_rechecks = 0,
-             int64_t *first_hit_host = nullptr);
+             int64_t *first_hit_host = nullptr, double *xnorm_hist_host = nullptr, int64_t xnorm_cap = 0);
+// xnorm_hist_host[k - 1] = ||x_k|| for k <= xnorm_cap: what scipy's `callback(x)` of the reference's verbose solvers
+// prints (ref main/example1/utils.py:104-106).
 
 }  // namespace mwx

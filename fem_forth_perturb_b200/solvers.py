@@ -356,10 +356,12 @@ class AMGHierarchy:
             pass
 
 
-def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=None, max_rechecks=0, monitor=None):
+def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=None, max_rechecks=0, monitor=None,
+        history=None):
     """Device PCG with scipy-1.4.1 semantics on a DeviceCSR / scipy matrix.  ``amg`` = a prebuilt
     :class:`AMGHierarchy` (hierarchy reuse across solves: north_star's "built once as timed setup"), else Jacobi /
-    plain CG.  ``b`` numpy or device tensor.  Returns (x as a device tensor, iters, info, resid)."""
+    plain CG.  ``b`` numpy or device tensor.  Returns (x as a device tensor, iters, info, resid).
+    ``history`` = a list: receives ||x_k|| of every iteration (what the reference's ``verbose=True`` callback prints)."""
     torch = L.require_cuda()
     A = _to_device_csr(A)
     n = A.shape[0]
@@ -373,7 +375,18 @@ def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=No
     work = torch.empty(4 * n, dtype=torch.float64, device=dev)
     iters, info, resid = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_double(0.0)
     mi = 0 if maxiter is None else int(maxiter)
-    if amg is None:
+    hist = None
+    if history is not None:
+        hist = np.zeros(max(1, min(mi if mi > 0 else 10 * n, 1000000)), dtype=np.float64)
+    if hist is not None and amg is None:
+        rc = L.lib().mwx_pcg_jacobi_history(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd), L.ptr(x),
+                                            float(tol), mi, 1 if precondition else 0, L.ptr(work), ctypes.byref(iters),
+                                            ctypes.byref(info), ctypes.byref(resid), L.ptr(hist), hist.size, L.stream())
+    elif hist is not None:
+        rc = L.lib().mwx_pcg_amg_history(amg._dev, n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd),
+                                         L.ptr(x), float(tol), mi, L.ptr(work), ctypes.byref(iters), ctypes.byref(info),
+                                         ctypes.byref(resid), L.ptr(hist), hist.size, L.stream())
+    elif amg is None:
         rc = L.lib().mwx_pcg_jacobi(n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(bd), L.ptr(x),
                                     float(tol), mi, 1 if precondition else 0, L.ptr(work), ctypes.byref(iters),
                                     ctypes.byref(info), ctypes.byref(resid), L.stream())
@@ -394,6 +407,8 @@ def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=No
         L.check(rc, 'mwx_pcg')
     if ro is not None:
         x = ro.backward(x)
+    if hist is not None:
+        history.extend(hist[:min(int(iters.value), hist.size)].tolist())
     return x, int(iters.value), int(info.value), float(resid.value)
 
 
@@ -433,7 +448,11 @@ def _make_krylov(print_iters, krylov=None, verbose=False, **kwargs):
         t0 = time.perf_counter()
         A = _to_device_csr(A)
         ro = Reordering.for_matrix(A) if reorder else None
-        x, it, info, resid = _run_pcg(A, b, kw.get('tol', 1e-5), kw.get('maxiter'), precondition=pre, reordering=ro)
+        hist = [] if verbose else None             # verbose: the reference's callback prints ||x_k|| every iteration
+        x, it, info, resid = _run_pcg(A, b, kw.get('tol', 1e-5), kw.get('maxiter'), precondition=pre, reordering=ro,
+                                      history=hist)
+        for v in hist or ():
+            print(v)
         solver.last = dict(iters=it, info=info, resid=resid, solve_seconds=time.perf_counter() - t0)
         if print_iters:
             print('cg', 'total interation steps:', it)
@@ -474,7 +493,10 @@ def _make_mgcg(print_iters, krylov=None, verbose=False, mode='parity', degree=2,
         t0 = time.perf_counter()
         ml = AMGHierarchy(A_d, mode=mode, degree=degree)          # rebuilt per solve, like the reference
         t1 = time.perf_counter()
-        x, it, info, resid = _run_pcg(A_d, b, kw.get('tol', 1e-5), kw.get('maxiter'), amg=ml)
+        hist = [] if verbose else None             # verbose: the reference's callback prints ||x_k|| every iteration
+        x, it, info, resid = _run_pcg(A_d, b, kw.get('tol', 1e-5), kw.get('maxiter'), amg=ml, history=hist)
+        for v in hist or ():
+            print(v)
         solver.last = dict(iters=it, info=info, resid=resid, setup_seconds=t1 - t0,
                            solve_seconds=time.perf_counter() - t1, levels=ml.level_sizes(), mode=mode)
         if print_iters:

@@ -307,6 +307,19 @@ int mwx_pcg_amg_monitored(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, co
                           int32_t max_rechecks, double *work, int64_t *iters_host, int32_t *info_host,
                           double *resid_host, int64_t *first_hit_host, void *stream);
 
+/* ``verbose=True`` of the reference's solver factories (ref main/example1/utils.py:104-110, 146-152, 229-235, 282-288):
+ * scipy calls ``callback(x)`` after every iteration and the reference prints ``np.linalg.norm(x)``.  Same solves as
+ * mwx_pcg_amg / mwx_pcg_jacobi; xnorm_hist_host[k-1] = ||x_k||_2 for the first xnorm_cap iterations (one extra dot
+ * per iteration, read back with the residual), printed by the Python closure. */
+int mwx_pcg_amg_history(mwx_amg_dev_t *d, int64_t n, const int64_t *indptr, const int32_t *indices,
+                        const double *values, const double *b, double *x, double tol, int64_t maxiter,
+                        double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
+                        double *xnorm_hist_host, int64_t xnorm_cap, void *stream);
+int mwx_pcg_jacobi_history(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                           const double *b, double *x, double tol, int64_t maxiter, int32_t precondition,
+                           double *work, int64_t *iters_host, int32_t *info_host, double *resid_host,
+                           double *xnorm_hist_host, int64_t xnorm_cap, void *stream);
+
 /* ------------------------------------------------------------------ callers either side of the hot path
  * K1 = asm(laplace, basis['w']) for P1 (ndpe 3) / P2 (ndpe 6), ref main/example1/run.py:149-154,198 (closed form). */
 int mwx_assemble_lagrange_laplace(int64_t nrows, int64_t nt, int32_t ndpe, const double *pxy, const int32_t *t,

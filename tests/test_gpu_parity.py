@@ -397,6 +397,28 @@ def test_pcg_jacobi_matches_oracle_cg(cuda, level, eps):
     assert abs(it_p - it_po) <= max(1, it_po // 20)        # hundreds of its: round-off sensitive
 
 
+def test_verbose_prints_the_iterate_norms_like_the_reference_callback(cuda, capsys):
+    """``verbose=True``: scipy calls ``callback(x)`` every iteration and the reference prints ``np.linalg.norm(x)``
+    (ref main/example1/utils.py:104-110, 229-235); here the norms are recorded on the device and printed after the solve."""
+    import fem_forth_perturb_b200 as F
+    om = OMesh().refine(4)
+    S = pl.solve_problem(om, pl.Ex1(1e-2), wkind='P1', intorder=5, return_system=True)
+    Kc, bc = S['Kc'], S['bc']
+    norms = []
+    x_or, info_or, it_or = cg141(Kc, bc, M=o_pc_diag(Kc), tol=1e-8, callback=lambda x: norms.append(np.linalg.norm(x)))
+    for factory, kw in ((F.solver_iter_krylov, dict(Precondition=True)), (F.solver_iter_mgcg, dict())):
+        capsys.readouterr()
+        solver = factory(verbose=True, tol=1e-8, **kw)
+        x, it = solver.solve_with_info(Kc, bc)
+        lines = capsys.readouterr().out.strip().splitlines()
+        assert lines[-1] == 'cg converged to tol=1e-08 and atol=default'
+        printed = np.array([float(v) for v in lines[:-1]])
+        assert len(printed) == it
+        assert abs(printed[-1] - np.linalg.norm(x)) <= 1e-12 * printed[-1]
+        if factory is F.solver_iter_krylov:                       # same algorithm as the oracle: same sequence of norms
+            assert it == it_or and np.allclose(printed, norms[:it], rtol=1e-9)
+
+
 def test_pcg_edge_cases(cuda):
     import fem_forth_perturb_b200 as F
     A = sp.diags([2.0] * 6).tocsr()
