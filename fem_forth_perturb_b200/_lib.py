@@ -93,6 +93,7 @@ _SIGNATURES = {
     'mwx_amg_dev_level_aux': [vp, i32, vp, _pi64, _pi32, vp, _pi32, vp],
     'mwx_amg_level_rho': [vp, i32, _pf64],
     'mwx_amg_set_chebyshev': [vp, i32, f64],
+    'mwx_amg_set_cycle': [vp, i32, i32, i32],
     'mwx_amg_destroy_dev': [vp],
     'mwx_amg_vcycle': [vp, vp, vp, vp],
     'mwx_pcg_amg_monitored': [vp, i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, _pi64, vp],

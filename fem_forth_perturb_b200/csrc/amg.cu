@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -162,6 +163,11 @@ __global__ void k_scale_by(int64_t n, const double *__restrict__ a, const double
         out[i] = c * (s ? s[i] : 1.0) * a[i];
 }
 
+__global__ void k_add_into(int64_t n, const double *__restrict__ a, double *__restrict__ x) {
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st) x[i] += a[i];
+}
+
 __global__ void k_cheby_first_zero(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv,
                                    double c2, double *__restrict__ x, double *__restrict__ d) {
     const int64_t st = (int64_t)gridDim.x * blockDim.x;
@@ -270,6 +276,7 @@ inline unsigned vgrid(int64_t n) {
 }  // namespace
 
 void free_csr(DCsr &m) {
+    free_bsr(m.bsr);
     if (!m.borrowed) { cudaFree(m.ptr); cudaFree(m.idx); cudaFree(m.val); }
     m = DCsr();
 }
@@ -290,7 +297,7 @@ extern "C" void mwx_amg_destroy_dev(mwx_amg_dev_t *d) {
         for (GsSweep *g : {&L.gs_f, &L.gs_b}) {
             cudaFree(g->wave_ptr); cudaFree(g->rows); cudaFree(g->col); cudaFree(g->val); cudaFree(g->diag);
         }
-        cudaFree(L.roots); cudaFree(L.cand);
+        cudaFree(L.roots); cudaFree(L.cand); cudaFree(L.g_b); cudaFree(L.g_x);
     }
     cudaFree(d->pinv); cudaFree(d->sc); cudaFree(d->partials);
     delete d;
@@ -362,6 +369,20 @@ int mwx::amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_ho
                 return MWX_E_NOMEM;
         }
     }
+    // block-CSR twins (bsr.cu) for the operators of a smoothed-aggregation hierarchy built on 3 candidates; an operator
+    // that fails the structure check simply keeps the scalar kernel.  MWX_BSR=0 switches them off (A/B runs).
+    const char *bsr_env = std::getenv("MWX_BSR");
+    const bool use_bsr = !bsr_env || std::atoi(bsr_env) != 0;
+    if (use_bsr && d->smoother != 0)
+        for (int l = 0; l + 1 < nl; ++l) {
+            DLevel &L = d->lv[(size_t)l];
+            if (L.coarse_per_root != 3) continue;
+            const int br = l == 0 ? 1 : 3;
+            if (!L.P.bsr.bptr && (rc = bsr_from_csr(L.P, br, 3, L.P.bsr, st))) return rc;
+            if (!L.R.bsr.bptr && (rc = bsr_from_csr(L.R, 3, br, L.R.bsr, st))) return rc;
+            DLevel &C = d->lv[(size_t)l + 1];
+            if (l + 2 < nl && !C.A.bsr.bptr && (rc = bsr_from_csr(C.A, 3, 3, C.A.bsr, st))) return rc;
+        }
     auto download = [&](const DCsr &M, std::vector<int64_t> &ptr, std::vector<int32_t> &idx, std::vector<double> &val) {
         ptr.resize((size_t)M.rows + 1); idx.resize((size_t)M.nnz); val.resize((size_t)M.nnz);
         MWX_CUDA(cudaMemcpyAsync(ptr.data(), M.ptr, sizeof(int64_t) * ptr.size(), cudaMemcpyDeviceToHost, st));
@@ -470,6 +491,21 @@ extern "C" int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t
     return 0;
 }
 
+// Operator applications of the V-cycle: the block kernels where the operator has a block-CSR twin, else k_spmv.
+static int op_spmv(const DCsr &M, const double *x, double *y, cudaStream_t st) {
+    if (M.bsr.bptr) return bsr_spmv(M.bsr, x, y, st);
+    return launch_spmv(M.rows, M.plan, M.ptr, M.idx, M.val, x, y, nullptr, nullptr, nullptr, nullptr, st);
+}
+static int op_spmv_axpy(const DCsr &M, const double *x, double *y, const double *c, int sign, cudaStream_t st) {
+    if (M.bsr.bptr) return bsr_spmv_axpy(M.bsr, x, y, c, sign, st);
+    return launch_spmv_axpy(M.rows, M.plan, M.ptr, M.idx, M.val, x, y, c, sign, st);
+}
+static int op_smoother_step(const DCsr &M, const double *x_in, double *x_out, const double *b, const double *dinv,
+                            double *d, double c1, double c2, cudaStream_t st) {
+    if (M.bsr.bptr) return bsr_smoother_step(M.bsr, x_in, x_out, b, dinv, d, c1, c2, st);
+    return launch_smoother_step(M.rows, M.plan, M.ptr, M.idx, M.val, x_in, x_out, b, dinv, d, c1, c2, st);
+}
+
 // One smoothing pass on level l.  `x_is_zero`: the iterate is known to be zero (pre-smoothing).
 // Returns through *xp the buffer that holds the smoothed iterate (x or the level's ping-pong buffer).
 static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_is_zero, double **xp,
@@ -502,7 +538,7 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
                 k_cheby_first_zero<<<vgrid(n), 256, 0, st>>>(n, b, L.dinv, omega, cur, L.d);
                 MWX_LAUNCH_CHECK();
             } else {
-                if ((rc = launch_smoother_step(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, 0.0, omega, st))) return rc;
+                if ((rc = op_smoother_step(L.A, cur, alt, b, L.dinv, L.d, 0.0, omega, st))) return rc;
                 std::swap(cur, alt);
             }
         }
@@ -523,7 +559,7 @@ static int smooth(mwx_amg_dev *d, DLevel &L, double *x, const double *b, bool x_
                 k_cheby_first_zero<<<vgrid(n), 256, 0, st>>>(n, b, L.dinv, c2, cur, L.d);
                 MWX_LAUNCH_CHECK();
             } else {
-                if ((rc = launch_smoother_step(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, cur, alt, b, L.dinv, L.d, c1, c2, st))) return rc;
+                if ((rc = op_smoother_step(L.A, cur, alt, b, L.dinv, L.d, c1, c2, st))) return rc;
                 std::swap(cur, alt);
             }
         }
@@ -539,18 +575,26 @@ static int cycle(mwx_amg_dev *d, int l, double *x, const double *b, cudaStream_t
     int rc;
     double *xs = x;
     if ((rc = smooth(d, L, x, b, true, &xs, st))) return rc;
-    if ((rc = launch_spmv_axpy(n, L.A.plan, L.A.ptr, L.A.idx, L.A.val, xs, L.r, b, -1, st))) return rc;
+    if ((rc = op_spmv_axpy(L.A, xs, L.r, b, -1, st))) return rc;
     DLevel &C = d->lv[(size_t)l + 1];
     const int64_t nc = C.A.rows;
-    if ((rc = launch_spmv(nc, L.R.plan, L.R.ptr, L.R.idx, L.R.val, L.r, C.b, nullptr, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = op_spmv(L.R, L.r, C.b, st))) return rc;
     if (l + 1 == nl - 1) {
         k_dense_gemv<<<grid_for(nc * 32, 256), 256, 0, st>>>(nc, d->pinv, C.b, C.x);
         MWX_LAUNCH_CHECK();
     } else {
         if ((rc = cycle(d, l + 1, C.x, C.b, st))) return rc;
+        if (d->gamma == 2 && l + 1 >= d->gamma_first && l + 1 <= d->gamma_last && C.g_b && C.g_x) {
+            // second visit (W-cycle flavour): x_c += M_c^-1 (b_c - A_c x_c).  Two steps of the symmetric stationary
+            // iteration from zero = (2 M^-1 - M^-1 A M^-1) b: the preconditioner stays symmetric positive definite.
+            if ((rc = op_spmv_axpy(C.A, C.x, C.g_b, C.b, -1, st))) return rc;
+            if ((rc = cycle(d, l + 1, C.g_x, C.g_b, st))) return rc;
+            k_add_into<<<vgrid(nc), 256, 0, st>>>(nc, C.g_x, C.x);
+            MWX_LAUNCH_CHECK();
+        }
     }
     // x += P x_c   (in place on whichever buffer holds the iterate)
-    if ((rc = launch_spmv_axpy(n, L.P.plan, L.P.ptr, L.P.idx, L.P.val, C.x, xs, xs, +1, st))) return rc;
+    if ((rc = op_spmv_axpy(L.P, C.x, xs, xs, +1, st))) return rc;
     double *xo = xs;
     if (d->smoother == 0) {
         if ((rc = smooth(d, L, xs, b, false, &xo, st))) return rc;
@@ -640,6 +684,23 @@ extern "C" int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ra
     if (!d || degree < 1 || degree > 16 || !(ratio > 1.0)) return MWX_E_BADARG;
     d->degree = degree;
     d->cheb_ratio = ratio;
+    return 0;
+}
+
+extern "C" int mwx_amg_set_cycle(mwx_amg_dev_t *d, int32_t gamma, int32_t first_level, int32_t last_level) {
+    if (!d || (gamma != 1 && gamma != 2) || first_level < 1 || last_level < 0) return MWX_E_BADARG;
+    const int nl = (int)d->lv.size();
+    if (gamma == 2)
+        for (int l = first_level; l < nl - 1 && l <= last_level; ++l) {           // the coarsest level is a direct solve: never revisited
+            DLevel &L = d->lv[(size_t)l];
+            const size_t bytes = sizeof(double) * (size_t)L.A.rows;
+            if ((!L.g_b && cudaMalloc((void **)&L.g_b, bytes) != cudaSuccess) ||
+                (!L.g_x && cudaMalloc((void **)&L.g_x, bytes) != cudaSuccess))
+                return MWX_E_NOMEM;
+        }
+    d->gamma = gamma;
+    d->gamma_first = first_level;
+    d->gamma_last = last_level;
     return 0;
 }
 

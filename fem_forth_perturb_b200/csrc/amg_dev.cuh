@@ -7,6 +7,15 @@
 
 namespace mwx {
 
+// Block-CSR twin of an operator whose nonzeros come in br x bc blocks (bsr.cu): planes of nblocks doubles.
+struct DBsr {
+    int br = 0, bc = 0, lanes = 8;
+    int64_t nbrows = 0, nblocks = 0;
+    int64_t *bptr = nullptr;
+    int32_t *bidx = nullptr;
+    double *bval = nullptr;
+};
+
 struct DCsr {
     int64_t rows = 0, cols = 0, nnz = 0;
     int64_t plan = -1;                         // -(planned SpMV tile height), see spmv_plan_rows
@@ -14,6 +23,7 @@ struct DCsr {
     int64_t *ptr = nullptr;
     int32_t *idx = nullptr;
     double *val = nullptr;
+    DBsr bsr;                                  // set (bptr != nullptr) when the V-cycle should use the block kernels
 };
 
 // One direction of the exact lexicographic Gauss-Seidel sweep, level-scheduled: rows grouped by dependency wavefront,
@@ -35,6 +45,7 @@ struct DLevel {
     // parity mode: the operator packed in Gauss-Seidel wavefront order, once per sweep direction (see GsSweep)
     GsSweep gs_f, gs_b;
     double rho = 0.0;                   // estimate of the spectral radius of D^-1 A
+    double *g_b = nullptr, *g_x = nullptr;   // right-hand side / correction of the second visit of a gamma = 2 cycle
     // smoothed-aggregation levels built on the device keep what the partitioned solver asks for
     int64_t *roots = nullptr;           // first fine DOF of every aggregate (ascending)
     int64_t nroots = 0;
@@ -44,6 +55,12 @@ struct DLevel {
 };
 
 void free_csr(DCsr &m);
+void free_bsr(DBsr &B);
+int bsr_from_csr(const DCsr &A, int br, int bc, DBsr &out, cudaStream_t st);
+int bsr_spmv(const DBsr &B, const double *x, double *y, cudaStream_t st);
+int bsr_spmv_axpy(const DBsr &B, const double *x, double *y, const double *c, int sign, cudaStream_t st);
+int bsr_smoother_step(const DBsr &B, const double *x_in, double *x_out, const double *b, const double *dinv, double *d,
+                      double c1, double c2, cudaStream_t st);
 
 // Work vectors, inverse diagonals, SpMV plans and (fast smoothers) spectral-radius estimates of every level whose
 // operators are already on the device; dense pseudo-inverse of the coarsest operator (coarse_pinv_host, or computed
@@ -56,6 +73,7 @@ struct mwx_amg_dev {
     int64_t n_last = 0;
     int smoother = 0, degree = 2;
     double cheb_ratio = 10.0;
+    int gamma = 1, gamma_first = 1, gamma_last = 0;    // gamma = 2: levels gamma_first .. gamma_last are visited twice per visit of their parent
     mwx::CgScalars *sc = nullptr;
     double *partials = nullptr;
 };

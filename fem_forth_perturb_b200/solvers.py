@@ -202,6 +202,7 @@ class AMGHierarchy:
                 Ac = self.level_matrix(self.levels - 1, 0).toarray()
                 pinv = self._pinv2(Ac)
                 L.check(lib.mwx_amg_dev_finalize(self._dev, L.ptr(pinv), L.stream()), 'mwx_amg_dev_finalize')
+                self._default_cycle()
             torch.cuda.synchronize()
             self.setup_host_seconds = 0.0
             self.setup_device_seconds = time.perf_counter() - t0
@@ -235,6 +236,19 @@ class AMGHierarchy:
         torch.cuda.synchronize()
         self.upload_seconds = time.perf_counter() - t1
 
+    def _default_cycle(self):
+        """Mode 'sa': levels 2.. with at least 10 000 rows are visited twice per visit of their parent (gamma = 2 there, a
+        V-cycle above and below).  Measured at 67 M DOFs (profiles/r02_gamma_cycle_*.json): 25 instead of 39 iterations for
+        17 % more time per iteration.  Level 1 is too expensive to revisit, the tiny levels are launch-latency bound.
+        MWX_SA_CYCLE=v keeps the plain V-cycle."""
+        import os
+        if os.environ.get('MWX_SA_CYCLE', 'k') == 'v':
+            return
+        sizes = self.level_sizes()
+        last = max([l for l in range(2, self.levels - 1) if sizes[l] >= 10000], default=0)
+        if last >= 2:
+            self.set_cycle(2, last, first=2)
+
     def _check_coarsest(self):
         if self.level_dims(self.levels - 1, 0)[0] > 8192:
             raise RuntimeError(f"AMG coarsening stopped at {self.level_dims(self.levels - 1, 0)[0]} rows (levels "
@@ -250,6 +264,10 @@ class AMGHierarchy:
 
     def set_chebyshev(self, degree=2, ratio=10.0):
         L.check(L.lib().mwx_amg_set_chebyshev(self._dev, int(degree), float(ratio)), 'mwx_amg_set_chebyshev')
+
+    def set_cycle(self, gamma=1, last=0, first=1):
+        """gamma = 2: levels ``first``..``last`` are visited twice per visit of their parent (still an SPD preconditioner)."""
+        L.check(L.lib().mwx_amg_set_cycle(self._dev, int(gamma), int(first), int(last)), 'mwx_amg_set_cycle')
 
     def level_dims(self, level, which=0):
         dims = np.zeros(3, dtype=np.int64)

@@ -286,6 +286,11 @@ int mwx_amg_dev_level_aux(const mwx_amg_dev_t *d, int32_t level, int64_t *roots,
 /* Chebyshev smoother: polynomial degree and eigenvalue interval [1.1 rho / ratio, 1.1 rho] (default 2, 10; tuned on the
  * level-11/12 meshes, profiles/r01_tune_amg.txt). */
 int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ratio);
+/* Cycle shape.  gamma = 1: V(1,1) (pyamg's default, what the reference uses).  gamma = 2 (fast modes only; no
+ * reference counterpart): levels first_level .. last_level (>= 1; the coarsest level is a direct solve and never
+ * revisited) are visited twice per visit of their parent - the second visit solves for the residual of the first, so
+ * the cycle is still a symmetric positive definite preconditioner for CG. */
+int mwx_amg_set_cycle(mwx_amg_dev_t *d, int32_t gamma, int32_t first_level, int32_t last_level);
 /* Estimated spectral radius of D^-1 A on a level (fast-mode smoothers; 0 in parity mode). */
 int mwx_amg_level_rho(const mwx_amg_dev_t *d, int32_t level, double *rho_host);
 void mwx_amg_destroy_dev(mwx_amg_dev_t *d);
