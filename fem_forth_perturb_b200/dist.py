@@ -833,6 +833,20 @@ class DistAMG:
             self.tail = AMGHierarchy(tail, mode='chebyshev', degree=self.degree, max_levels=max(1, max_levels - lsw),
                                      reorder=False)
         self.tail.set_chebyshev(self.degree, self.ratio)
+        self._tail_matrix = tail
+        # Cycle shape of mode 'sa' as on one GPU (AMGHierarchy._default_cycle): GLOBAL levels 2 .. `last` (the last one
+        # with at least 10 000 rows) are visited twice per visit of their parent.  Distributed levels are revisited by
+        # _cycle, the first replicated level inside the tail step, the rest by the tail hierarchy's own cycle setting.
+        self.revisit = ()
+        if mode == 'sa' and os.environ.get('MWX_SA_CYCLE', 'k') != 'v':
+            sizes = [o[-1] for o in offs[:lsw]] + self.tail.level_sizes()
+            min_rows = int(os.environ.get('MWX_SA_CYCLE_MIN_ROWS', 10000))
+            last = max([g for g in range(2, len(sizes) - 1) if sizes[g] >= min_rows], default=0)
+            self.revisit = tuple(range(2, last + 1))
+            self.tail.set_cycle(1, 0)
+            if last - lsw >= 1:
+                self.tail.set_cycle(2, last - lsw, first=max(1, 2 - lsw))
+        self._cur_ext = {}
         # ---- per level work vectors, inverse diagonals, spectral radius estimates
         ops = self.ops
         for l, lv in enumerate(self.levels):
@@ -844,6 +858,9 @@ class DistAMG:
             lv['bc'] = [ops.zeros(r.nloc, dev) for r in lv['R']]
             lv['xc'] = [comm.ext_zeros(p_, dev) for p_ in lv['P']]                  # coarse iterate, P's column layout
             lv['rho'] = self._estimate_rho(lv)
+            if l in self.revisit:
+                lv['g_b'] = [ops.zeros(a.nloc, dev) for a in lv['A']]
+                lv['g_x'] = [ops.zeros(a.nloc, dev) for a in lv['A']]
 
     # power iteration on D^-1 A (collective; deterministic start)
     def _estimate_rho(self, lv):
@@ -928,6 +945,8 @@ class DistAMG:
                 full = self.comm.allgather(b, self.offsets[l])
                 for part_idx, f in enumerate(full):
                     z = self.tail.precondition(f)
+                    if l in self.revisit:                       # second visit of the first replicated level
+                        z = z + self.tail.precondition(f - self._tail_matrix.dot(z))
                     r = self.parts[part_idx].rank
                     self._tail_out[part_idx].copy_(z[self.offsets[l][r]:self.offsets[l][r + 1]])
             self._host_step(tail_step)
@@ -941,6 +960,24 @@ class DistAMG:
         for R, r, bc in zip(lv['R'], lv['r'], lv['bc']):
             ops.spmv(R, r, bc)
         xc = self._cycle(l + 1, lv['bc'])
+        if l + 1 < self.lsw and (l + 1) in self.revisit:        # second visit: x_c += M^-1 (b_c - A x_c), still SPD
+            lvm = self.levels[l + 1]
+            cur_m = self._cur_ext[l + 1]
+            comm.halo(lvm['A'], cur_m)
+            for a, x, bi, gb in zip(lvm['A'], cur_m, lv['bc'], lvm['g_b']):
+                ops.spmv_axpy(a, x, bi, -1, gb)
+
+            def save(xc=xc, lvm=lvm):                           # the nested cycle reuses the level's work vectors
+                for gx, x_c in zip(lvm['g_x'], xc):
+                    gx.copy_(x_c)
+            self._host_step(save)
+            x2 = self._cycle(l + 1, lvm['g_b'])
+
+            def accumulate(x2=x2, lvm=lvm):
+                for gx, d in zip(lvm['g_x'], x2):
+                    gx.add_(d)
+            self._host_step(accumulate)
+            xc = lvm['g_x']
 
         def fill_coarse(lv=lv, xc=xc):
             for P, xce, x_c in zip(lv['P'], lv['xc'], xc):
@@ -950,6 +987,7 @@ class DistAMG:
         for P, xce, x in zip(lv['P'], lv['xc'], cur):
             ops.spmv_axpy(P, xce, x, +1, x)                     # x += P x_c (owned rows)
         cur, alt = self._smooth(lv, cur, alt, b, False, comm)
+        self._cur_ext[l] = cur
         return [x[:a.nloc] for a, x in zip(lv['A'], cur)]
 
     def apply(self, r_list):

@@ -245,7 +245,8 @@ class AMGHierarchy:
         if os.environ.get('MWX_SA_CYCLE', 'k') == 'v':
             return
         sizes = self.level_sizes()
-        last = max([l for l in range(2, self.levels - 1) if sizes[l] >= 10000], default=0)
+        min_rows = int(os.environ.get('MWX_SA_CYCLE_MIN_ROWS', 10000))
+        last = max([l for l in range(2, self.levels - 1) if sizes[l] >= min_rows], default=0)
         if last >= 2:
             self.set_cycle(2, last, first=2)
 

@@ -190,17 +190,22 @@ def test_partitioned_pcg_independent_of_partition_count(cuda):
 
 
 @pytest.mark.gpu
-def test_distributed_smoothed_aggregation_matches_single_gpu(cuda):
-    """mode='sa' through the partitioned V-cycle: aggregates are numbered by seed, so coarse levels stay row-blocked."""
+@pytest.mark.parametrize('min_rows,switch_rows', [(10000, 600), (50, 100), (50, 600), (50, 3000)])
+def test_distributed_smoothed_aggregation_matches_single_gpu(cuda, monkeypatch, min_rows, switch_rows):
+    """mode='sa' through the partitioned V-cycle: aggregates are numbered by seed, so coarse levels stay row-blocked.
+    min_rows = 50 turns the gamma = 2 revisit of level 2 on at this problem size: with that level row-blocked
+    (switch_rows 100), as the first replicated level (600: revisited inside the tail step) and as a level inside the
+    replicated tail hierarchy (3000)."""
     torch = cuda
+    monkeypatch.setenv('MWX_SA_CYCLE_MIN_ROWS', str(min_rows))
     F, D, prob, Kc = _setup(6, 3, eps2=0.25)
     from fem_forth_perturb_b200.solvers import Reordering, _run_pcg
     ro = Reordering.for_matrix(Kc)
     ro.perm, ro.iperm = prob.partition.perm, prob.partition.iperm
     Kp = ro.matrix(Kc)
     assert Kp.candidates is not None
-    amg = D.DistAMG(prob.parts, prob.comm, Kp, mode='sa', switch_rows=600)
-    assert amg.lsw >= 1
+    amg = D.DistAMG(prob.parts, prob.comm, Kp, mode='sa', switch_rows=switch_rows)
+    assert amg.lsw >= 1 and (len(amg.revisit) > 0) == (min_rows == 50)
     rng = np.random.default_rng(4)
     b_new = torch.from_numpy(rng.standard_normal(Kc.shape[0])).cuda()
     single = F.AMGHierarchy(Kp, mode='sa', reorder=False)
