@@ -126,13 +126,13 @@ __global__ void k_strength(int64_t nn, int bs, double theta, const int64_t *__re
 constexpr unsigned long long KEY_ROOT = ~0ull;
 
 __global__ void k_mis_keys(int64_t nn, const int64_t *__restrict__ Sp, unsigned long long *__restrict__ key,
-                           int8_t *__restrict__ state) {
+                           int8_t *__restrict__ state, unsigned long long hash_mask) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     const int64_t deg = Sp[i + 1] - Sp[i];
     uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
     h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-    key[i] = ((unsigned long long)(deg < 254 ? deg + 1 : 255) << 56) | ((unsigned long long)(h & 0xFFFFFFull) << 32) |
+    key[i] = ((unsigned long long)(deg < 254 ? deg + 1 : 255) << 56) | ((unsigned long long)(h & hash_mask) << 32) |
              (unsigned long long)(uint32_t)i;
     state[i] = 0;
 }
@@ -563,7 +563,12 @@ int build_aggregates(const DCsr &A, int bs, double theta, const double *dn, Leve
     MWX_CUDA(m1.alloc((size_t)nn));
     MWX_CUDA(m2.alloc((size_t)nn));
     MWX_CUDA(state.alloc((size_t)nn));
-    k_mis_keys<<<gn, 256, 0, st>>>(nn, sp.p, key.p, state.p);
+    static const unsigned long long hash_mask = [] {
+        const char *e = std::getenv("MWX_SA_MIS_HASH_BITS");
+        const int bits = e ? std::atoi(e) : 24;
+        return bits <= 0 ? 0ull : (bits >= 24 ? 0xFFFFFFull : ((1ull << bits) - 1ull));
+    }();
+    k_mis_keys<<<gn, 256, 0, st>>>(nn, sp.p, key.p, state.p, hash_mask);
     MWX_LAUNCH_CHECK();
     for (int round = 0;; ++round) {
         if (round > 500) return MWX_E_NOCONV;

@@ -838,7 +838,13 @@ class DistAMG:
         # with at least 10 000 rows) are visited twice per visit of their parent.  Distributed levels are revisited by
         # _cycle, the first replicated level inside the tail step, the rest by the tail hierarchy's own cycle setting.
         self.revisit = ()
-        if mode == 'sa' and os.environ.get('MWX_SA_CYCLE', 'k') != 'v':
+        # Only where a rank's share of the fine level is large (>= 2^24 rows): the revisited levels are small, their cost
+        # does not shrink with the number of ranks (halo latencies, the replicated tail), and at 8 GPUs / 67 M DOFs the
+        # revisits cost more (8.9 ms x 25 iterations) than the plain V-cycle (4.9 ms x 40) - MWX_SA_CYCLE=k forces them.
+        cycle_env = os.environ.get('MWX_SA_CYCLE', 'auto')
+        want = cycle_env == 'k' or (cycle_env == 'auto' and offs[0][-1] // max(world, len(parts)) >= (1 << 24)) or \
+            ('MWX_SA_CYCLE_MIN_ROWS' in os.environ and cycle_env != 'v')
+        if mode == 'sa' and want:
             sizes = [o[-1] for o in offs[:lsw]] + self.tail.level_sizes()
             min_rows = int(os.environ.get('MWX_SA_CYCLE_MIN_ROWS', 10000))
             last = max([g for g in range(2, len(sizes) - 1) if sizes[g] >= min_rows], default=0)

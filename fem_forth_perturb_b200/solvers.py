@@ -242,7 +242,7 @@ class AMGHierarchy:
         17 % more time per iteration.  Level 1 is too expensive to revisit, the tiny levels are launch-latency bound.
         MWX_SA_CYCLE=v keeps the plain V-cycle."""
         import os
-        if os.environ.get('MWX_SA_CYCLE', 'k') == 'v':
+        if os.environ.get('MWX_SA_CYCLE', 'auto') == 'v':
             return
         sizes = self.level_sizes()
         min_rows = int(os.environ.get('MWX_SA_CYCLE_MIN_ROWS', 10000))
