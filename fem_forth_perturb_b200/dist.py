@@ -841,16 +841,17 @@ class DistAMG:
         # Only where a rank's share of the fine level is large (>= 2^24 rows): the revisited levels are small, their cost
         # does not shrink with the number of ranks (halo latencies, the replicated tail), and at 8 GPUs / 67 M DOFs the
         # revisits cost more (8.9 ms x 25 iterations) than the plain V-cycle (4.9 ms x 40) - MWX_SA_CYCLE=k forces them.
+        # Smaller shares revisit only the REPLICATED levels (inside the tail step: no extra halo or all-gather).
         cycle_env = os.environ.get('MWX_SA_CYCLE', 'auto')
-        want = cycle_env == 'k' or (cycle_env == 'auto' and offs[0][-1] // max(world, len(parts)) >= (1 << 24)) or \
-            ('MWX_SA_CYCLE_MIN_ROWS' in os.environ and cycle_env != 'v')
-        if mode == 'sa' and want:
+        everywhere = cycle_env == 'k' or 'MWX_SA_CYCLE_MIN_ROWS' in os.environ or \
+            offs[0][-1] // max(world, len(parts)) >= (1 << 24)
+        if mode == 'sa' and cycle_env != 'v':
             sizes = [o[-1] for o in offs[:lsw]] + self.tail.level_sizes()
             min_rows = int(os.environ.get('MWX_SA_CYCLE_MIN_ROWS', 10000))
             last = max([g for g in range(2, len(sizes) - 1) if sizes[g] >= min_rows], default=0)
-            self.revisit = tuple(range(2, last + 1))
+            self.revisit = tuple(range(2 if everywhere else max(2, lsw), last + 1))
             self.tail.set_cycle(1, 0)
-            if last - lsw >= 1:
+            if last - lsw >= 1 and self.revisit:
                 self.tail.set_cycle(2, last - lsw, first=max(1, 2 - lsw))
         self._cur_ext = {}
         # ---- per level work vectors, inverse diagonals, spectral radius estimates
