@@ -779,7 +779,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     Dset = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
     t0 = time.perf_counter()
     # halo exchange: pack-and-push kernels into the neighbours' peer memory over NVLink (MWX_HALO=nccl: send/recv)
-    comm = D.TorchDistComm() if os.environ.get('MWX_HALO', 'peer') == 'nccl' else D.SymmMemComm()
+    halo_kind = os.environ.get('MWX_HALO', 'peer')
+    comm = {'nccl': D.TorchDistComm, 'symm': D.SymmMemComm, 'peer': D.PeerComm}[halo_kind]()
     prob = D.PartitionedProblem(basis, Dset, comm).assemble(form)
     (p,) = prob.parts
     torch.cuda.synchronize()
@@ -885,13 +886,17 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
                                f'eps={EPS}, tol={TOL}, rhs=K2c@x*; preconditioner = global ' + ('smoothed-aggregation' if amg_mode == 'sa' else 'RS-AMG') + ' hierarchy applied as a '
                                f'collective Chebyshev V-cycle ({ml.lsw} row-blocked levels, tail of {nlev - ml.lsw} levels '
                                f'replicated); halo = '
-                               + ('NCCL send/recv' if isinstance(comm, D.TorchDistComm) and not isinstance(comm, D.SymmMemComm) else 'pack-and-push kernels into peer memory over NVLink + signal-pad barrier') + ', all-reduces over NCCL',
+                               + {'nccl': 'NCCL send/recv, all-reduces over NCCL', 'symm': 'pack-and-push kernels into peer memory over NVLink + signal-pad barrier, all-reduces over NCCL',
+                                  'peer': 'every exchange of the iteration (halo push fused with the barrier, all-reduce of the CG scalars, all-gather for the replicated tail) is a kernel storing into peer memory over NVLink; iterations 2.. are one CUDA-graph launch each'}[halo_kind],
                    'l2': 'per-rank operator exceeds the 126 MB L2 for level >= 11; 256 MiB written before the SpMV sample'},
         'assembly_mdof_s': N / (float(phmax[0]) * 1e-3) / 1e6, 'assembly_ms': float(phmax[0]),
         'pcg': {'s_per_solve': float(phmax[2]) * 1e-3, 'iters': iters, 'info': rs[-1]['info'], 'mode': f'distributed {amg_mode} hierarchy, Chebyshev V-cycle',
                 'ms_per_iter': float(phmax[2]) / max(iters, 1),
                 'rel_err_vs_manufactured': float(torch.sqrt(err2[0] / err2[1])),
-                'level_offsets': [o[-1] for o in ml.offsets], 'distributed_levels': ml.lsw, 'levels': nlev},
+                'level_offsets': [o[-1] for o in ml.offsets], 'distributed_levels': ml.lsw, 'levels': nlev,
+                'revisited_levels': list(getattr(ml, 'revisit', ())),
+                'block_csr_operators': sum(1 for lv in ml.levels for k in 'APR' for op in lv[k] if getattr(op, 'bsr', None)),
+                'cuda_graph': bool(getattr(comm, 'graphable', False)) and os.environ.get('MWX_DIST_GRAPH', '1') != '0'},
         'spmv': {'ms': float(phmax[1]), 'gbs_per_gpu': spmv_gbs_rank, 'frac_of_peak': spmv_gbs_rank / peak,
                  'note': 'local block of the slowest rank, halo not included'},
         'partition': {'rows_max': int(nloc_max), 'ghosts_max': int(phmax[5]), 'nnz_total': int(nnzc_glob)},

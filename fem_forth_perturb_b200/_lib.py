@@ -52,6 +52,15 @@ _SIGNATURES = {
     'mwx_dist_localize': [i64, vp, i32, i32, vp, i32, i32, vp, vp],
     'mwx_gather_f64_i64': [i64, vp, vp, vp, vp],
     'mwx_halo_push': [i64, i32, vp, vp, vp, vp, vp],
+    'mwx_bsr_create': [i64, i64, i64, vp, vp, vp, i32, i32, ctypes.POINTER(vp), vp],
+    'mwx_bsr_destroy': [vp],
+    'mwx_bsr_spmv': [vp, vp, vp, vp],
+    'mwx_bsr_spmv_axpy': [vp, vp, vp, i32, vp, vp],
+    'mwx_bsr_smoother_step': [vp, vp, vp, vp, vp, vp, f64, f64, vp],
+    'mwx_peer_ctl_bytes': [],
+    'mwx_peer_barrier': [vp, vp, i32, i32, i32, vp],
+    'mwx_peer_push': [i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    'mwx_peer_allreduce': [vp, i32, vp, vp, i32, i32, i32, vp],
     'mwx_dcg_workspace_doubles': [],
     'mwx_dcg_dot': [i64, vp, vp, vp, i32, vp],
     'mwx_dcg_p_update': [i64, vp, vp, vp, vp, vp, i32, vp],
@@ -101,7 +110,7 @@ _SIGNATURES = {
     'mwx_pcg_jacobi_history': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp, i64, vp],
     'mwx_pcg_amg': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp],
 }
-_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev', 'mwx_asm_plan_destroy'}
+_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev', 'mwx_asm_plan_destroy', 'mwx_bsr_destroy'}
 
 ERRORS = {-1: 'MWX_E_BADARG', -2: 'MWX_E_CAPACITY', -3: 'MWX_E_NOCONV', -4: 'MWX_E_NOMEM'}
 

@@ -377,7 +377,16 @@ int mwx::amg_finalize_device_levels(mwx_amg_dev *d, const double *coarse_pinv_ho
         for (int l = 0; l + 1 < nl; ++l) {
             DLevel &L = d->lv[(size_t)l];
             if (L.coarse_per_root != 3) continue;
-            const int br = l == 0 ? 1 : 3;
+            int br = l == 0 ? 1 : 3;
+            if (l == 0 && L.A.rows % 3 == 0 && L.A.nnz % 9 == 0 && !L.P.bsr.bptr) {
+                // the fine level of a TAIL hierarchy (replicated levels of the partitioned solver) is itself a coarse
+                // level of the scheme: its P has 3x3 blocks - the structure check tells (a scalar fine level fails it)
+                if ((rc = bsr_from_csr(L.P, 3, 3, L.P.bsr, st))) return rc;
+                if (L.P.bsr.bptr) {
+                    br = 3;
+                    if (!L.A.bsr.bptr && (rc = bsr_from_csr(L.A, 3, 3, L.A.bsr, st))) return rc;
+                }
+            }
             if (!L.P.bsr.bptr && (rc = bsr_from_csr(L.P, br, 3, L.P.bsr, st))) return rc;
             if (!L.R.bsr.bptr && (rc = bsr_from_csr(L.R, 3, br, L.R.bsr, st))) return rc;
             DLevel &C = d->lv[(size_t)l + 1];

@@ -212,7 +212,7 @@ int bsr_from_csr(const DCsr &A, int br, int bc, DBsr &out, cudaStream_t st) {
     k_bsr_fill<<<grid_for(nbrows, 256), 256, 0, st>>>(nbrows, nblocks, br, bc, A.ptr, A.idx, A.val, B.bptr, B.bidx, B.bval);
     MWX_LAUNCH_CHECK();
     const double avg = nbrows > 0 ? (double)nblocks / (double)nbrows : 0.0;
-    B.lanes = avg <= 6.0 ? 4 : avg <= 24.0 ? 8 : 16;
+    B.lanes = avg <= 6.0 ? 4 : avg <= 24.0 ? 8 : avg <= 96.0 ? 16 : 32;   // nearly dense tail levels: a whole warp per block row
     out = B;
     return 0;
 }
@@ -231,3 +231,42 @@ int bsr_smoother_step(const DBsr &B, const double *x_in, double *x_out, const do
 }
 
 }  // namespace mwx
+
+// ---- C ABI: block-CSR twins for operators held outside an AMG hierarchy (the row blocks of the partitioned V-cycle) ----
+extern "C" int mwx_bsr_create(int64_t rows, int64_t cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                              const double *values, int32_t br, int32_t bc, void **out, void *stream) {
+    if (!out) return MWX_E_BADARG;
+    *out = nullptr;
+    if (rows <= 0 || cols <= 0 || nnz <= 0 || !indptr || !indices || !values) return 0;
+    mwx::DCsr A;
+    A.rows = rows; A.cols = cols; A.nnz = nnz; A.borrowed = true;
+    A.ptr = const_cast<int64_t *>(indptr); A.idx = const_cast<int32_t *>(indices); A.val = const_cast<double *>(values);
+    mwx::DBsr B;
+    const int rc = mwx::bsr_from_csr(A, br, bc, B, mwx::as_stream(stream));
+    if (rc) return rc;
+    if (B.bptr) *out = new mwx::DBsr(B);
+    return 0;
+}
+
+extern "C" void mwx_bsr_destroy(void *b) {
+    if (!b) return;
+    mwx::DBsr *B = (mwx::DBsr *)b;
+    mwx::free_bsr(*B);
+    delete B;
+}
+
+extern "C" int mwx_bsr_spmv(const void *b, const double *x, double *y, void *stream) {
+    if (!b || !x || !y) return MWX_E_BADARG;
+    return mwx::bsr_spmv(*(const mwx::DBsr *)b, x, y, mwx::as_stream(stream));
+}
+
+extern "C" int mwx_bsr_spmv_axpy(const void *b, const double *x, const double *c, int32_t sign, double *y, void *stream) {
+    if (!b || !x || !y || !c || sign == 0) return MWX_E_BADARG;
+    return mwx::bsr_spmv_axpy(*(const mwx::DBsr *)b, x, y, c, sign, mwx::as_stream(stream));
+}
+
+extern "C" int mwx_bsr_smoother_step(const void *b, const double *x_in, double *x_out, const double *rhs,
+                                     const double *dinv, double *d, double c1, double c2, void *stream) {
+    if (!b || !x_in || !x_out || !rhs || !dinv || !d || x_in == x_out) return MWX_E_BADARG;
+    return mwx::bsr_smoother_step(*(const mwx::DBsr *)b, x_in, x_out, rhs, dinv, d, c1, c2, mwx::as_stream(stream));
+}

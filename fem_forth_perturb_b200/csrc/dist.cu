@@ -82,6 +82,106 @@ inline unsigned sgrid(int64_t n) {
     return (unsigned)(g < 1 ? 1 : g);
 }
 
+
+// ---------------------------------------------------------------- peer-memory collectives (one process per GPU)
+// Everything the partitioned iteration exchanges goes through kernels that store straight into the peers' memory over
+// NVLink: halo segments, the CG scalars (all-reduce) and the coarse residual (all-gather).  Synchronisation is a
+// barrier on monotonically increasing epoch flags that live in a small symmetric control block per rank; the epoch
+// counter itself is DEVICE-resident, so a captured CUDA graph of one iteration can be replayed any number of times and
+// mixed with eager launches (the barrier of torch's symmetric memory keeps its state on the host and cannot).
+constexpr int PEER_MAX_WORLD = 32;
+constexpr int PEER_MAX_SLOTS = 8;
+
+struct PeerCtl {
+    uint32_t flags[PEER_MAX_WORLD];   // flags[r]: last barrier epoch rank r has entered (written by rank r)
+    uint32_t epoch;                   // local: barriers entered so far
+    uint32_t nred;                    // local: all-reduces finished so far (selects the buffer half)
+    uint32_t done;                    // local: "last block" ticket of the fused push
+    uint32_t pad[PEER_MAX_WORLD - 3];
+    double red[2][PEER_MAX_WORLD][PEER_MAX_SLOTS];   // red[half][rank][slot], written by rank `rank`
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by ALL threads of one block (blockDim.x >= world).  wait = 0: signal only (all parts in one process on one
+// stream: stream order already is the barrier and a spin would never be released).
+__device__ void peer_barrier(PeerCtl *me, PeerCtl *const *peers, int rank, int world, int wait) {
+    __shared__ uint32_t e_sh;
+    __syncthreads();
+    if (threadIdx.x == 0) { e_sh = me->epoch + 1; me->epoch = e_sh; }
+    __syncthreads();
+    const uint32_t e = e_sh;
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(&peers[threadIdx.x]->flags[rank], e);
+        if (wait)
+            while ((int32_t)(ld_acquire_sys(&me->flags[threadIdx.x]) - e) < 0) { }
+    }
+    __syncthreads();
+}
+
+__global__ void k_peer_barrier(PeerCtl *me, PeerCtl *const *peers, int rank, int world, int wait) {
+    peer_barrier(me, peers, rank, world, wait);
+}
+
+// dst[s][i - seg[s]] = v[idx ? idx[i] : i - seg[s]]; the block that finishes last runs the barrier, so the exchange
+// is ONE launch: when it retires, every rank's pushes have landed.
+__global__ void __launch_bounds__(256) k_peer_push(int64_t total, int32_t nseg, const int64_t *__restrict__ seg,
+                                                   const int32_t *__restrict__ idx, const double *__restrict__ v,
+                                                   double *const *__restrict__ dst, PeerCtl *me, PeerCtl *const *peers,
+                                                   int rank, int world, int wait) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t s = 0;
+        while (s + 1 < nseg && i >= seg[s + 1]) ++s;
+        const int64_t k = i - seg[s];
+        dst[s][k] = v[idx ? (int64_t)idx[i] : k];
+    }
+    __shared__ int last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&me->done, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) me->done = 0;
+    }
+    __syncthreads();
+    if (last) peer_barrier(me, peers, rank, world, wait);
+}
+
+// vals[0..count) <- sum over ranks, added in rank order on every rank (bitwise identical results everywhere).
+// phase 0: write + barrier + sum; 1: write only; 2: sum only (the in-process driver runs 1 for all parts, then 2).
+__global__ void k_peer_allreduce(double *vals, int count, PeerCtl *me, PeerCtl *const *peers, int rank, int world,
+                                 int phase) {
+    const int half = (int)(me->nred & 1u);
+    if (phase != 2) {
+        for (int k = threadIdx.x; k < world * count; k += blockDim.x)
+            peers[k / count]->red[half][rank][k % count] = vals[k % count];
+    }
+    if (phase == 0) peer_barrier(me, peers, rank, world, 1);
+    if (phase != 1) {
+        __syncthreads();
+        if ((int)threadIdx.x < count) {
+            double s = 0.0;
+            for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(&me->red[half][r][threadIdx.x]);
+            vals[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) me->nred = me->nred + 1;
+    }
+}
+
 }  // namespace
 }  // namespace mwx
 
@@ -154,6 +254,40 @@ extern "C" int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *i
     if (n < 0 || (n && (!src || !idx || !dst))) return MWX_E_BADARG;
     if (n == 0) return 0;
     k_gather_f64_i64<<<sgrid(n), 256, 0, as_stream(stream)>>>(n, src, idx, dst);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_peer_ctl_bytes(void) { return (int)sizeof(PeerCtl); }
+
+static bool peer_args_ok(const void *ctl, const void *peers, int32_t rank, int32_t world) {
+    return ctl && peers && world >= 1 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world;
+}
+
+extern "C" int mwx_peer_barrier(void *ctl, const void *peers, int32_t rank, int32_t world, int32_t wait, void *stream) {
+    if (!peer_args_ok(ctl, peers, rank, world)) return MWX_E_BADARG;
+    k_peer_barrier<<<1, PEER_MAX_WORLD, 0, as_stream(stream)>>>((PeerCtl *)ctl, (PeerCtl *const *)peers, rank, world, wait);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_peer_push(int64_t total, int32_t nseg, const int64_t *seg, const int32_t *idx, const double *v,
+                             double *const *dst, void *ctl, const void *peers, int32_t rank, int32_t world,
+                             int32_t wait, void *stream) {
+    if (!peer_args_ok(ctl, peers, rank, world) || total < 0 || nseg < 0 || (total && (!seg || !v || !dst || nseg == 0)))
+        return MWX_E_BADARG;
+    k_peer_push<<<sgrid(total), 256, 0, as_stream(stream)>>>(total, nseg, seg, idx, v, dst, (PeerCtl *)ctl,
+                                                             (PeerCtl *const *)peers, rank, world, wait);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mwx_peer_allreduce(double *vals, int32_t count, void *ctl, const void *peers, int32_t rank,
+                                  int32_t world, int32_t phase, void *stream) {
+    if (!peer_args_ok(ctl, peers, rank, world) || !vals || count < 1 || count > PEER_MAX_SLOTS || phase < 0 || phase > 2)
+        return MWX_E_BADARG;
+    k_peer_allreduce<<<1, 256, 0, as_stream(stream)>>>(vals, count, (PeerCtl *)ctl, (PeerCtl *const *)peers, rank, world,
+                                                       phase);
     MWX_LAUNCH_CHECK();
     return 0;
 }

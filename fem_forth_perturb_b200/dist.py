@@ -100,10 +100,14 @@ class HaloPlan:
 class LocalOp(HaloPlan):
     """Rows [rlo, rhi) of a global CSR operator (device tensors), columns renumbered to [owned | ghost]."""
 
-    def __init__(self, indptr, indices, values, rlo, rhi, col_offsets, rank):
+    def __init__(self, indptr, indices, values, rlo, rhi, col_offsets, rank, block=None):
+        """block = (br, bc): also build the block-CSR twin (csrc/bsr.cu) when the local operator has that structure -
+        owned columns start at a block boundary and ghosts come in whole blocks for the operators of a
+        smoothed-aggregation hierarchy; the kernels behind CudaOps then use it (``self.bsr``)."""
         torch = L.require_cuda()
         dev = values.device
         self.rank, self.nloc = rank, rhi - rlo
+        self.bsr = None
         self.clo, self.ncol = col_offsets[rank], col_offsets[rank + 1] - col_offsets[rank]
         s0, s1 = int(indptr[rlo].item()), int(indptr[rhi].item())
         self.indptr = (indptr[rlo:rhi + 1] - s0).contiguous()
@@ -121,6 +125,19 @@ class LocalOp(HaloPlan):
             L.check(L.lib().mwx_spmv_plan(self.nloc, L.ptr(self.indptr), ctypes.byref(rows_plan), L.stream()), 'mwx_spmv_plan')
         self.spmv_hint = -int(rows_plan.value) if rows_plan.value else -1
         self._plan_ghosts(col_offsets, dev)
+        if block is not None and self.nnz > 0 and os.environ.get('MWX_BSR', '1') != '0':
+            h = ctypes.c_void_p()
+            L.check(L.lib().mwx_bsr_create(self.nloc, self.ncol + self.nghost, self.nnz, L.ptr(self.indptr), L.ptr(self.cols),
+                                           L.ptr(self.vals), int(block[0]), int(block[1]), ctypes.byref(h), L.stream()),
+                    'mwx_bsr_create')
+            self.bsr = h if h.value else None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'bsr', None):
+                L.lib().mwx_bsr_destroy(self.bsr)
+        except Exception:
+            pass
 
 
 class RankSystem(HaloPlan):
@@ -450,6 +467,185 @@ class SymmMemComm(TorchDistComm):
         self.last_halo[vp_] = self.epoch
 
 
+class _PeerKernels:
+    """Launchers of the peer-memory collectives (csrc/dist.cu: mwx_peer_push / mwx_peer_allreduce / mwx_peer_barrier).
+    They are plain kernel launches on the current stream with a device-resident barrier epoch, so a whole PCG
+    iteration built from them can be captured in a CUDA graph and replayed (``graphable``)."""
+    graphable = True
+
+    def _ctl_alloc(self, make):
+        """make(nbytes) -> zeroed device tensor (float64) of the control block."""
+        nbytes = L.lib().mwx_peer_ctl_bytes()
+        return make((nbytes + 7) // 8)
+
+    def _launch_push(self, rank, plan, v, wait):
+        total, nseg, seg, idx, dst = plan
+        rc = L.lib().mwx_peer_push(total, nseg, L.ptr(seg), L.ptr(idx), L.ptr(v), L.ptr(dst), L.ptr(self._ctl[rank]),
+                                   L.ptr(self._peer_table), rank, self.world, self._wait, L.stream())
+        if rc:
+            L.check(rc, 'mwx_peer_push')
+
+    def _launch_allreduce(self, rank, t, phase):
+        rc = L.lib().mwx_peer_allreduce(L.ptr(t), t.numel(), L.ptr(self._ctl[rank]), L.ptr(self._peer_table), rank,
+                                        self.world, phase, L.stream())
+        if rc:
+            L.check(rc, 'mwx_peer_allreduce')
+
+    def _launch_barrier(self, rank):
+        rc = L.lib().mwx_peer_barrier(L.ptr(self._ctl[rank]), L.ptr(self._peer_table), rank, self.world, self._wait,
+                                      L.stream())
+        if rc:
+            L.check(rc, 'mwx_peer_barrier')
+
+    @staticmethod
+    def _push_arrays(counts, idx_list, dst_ptrs, dev):
+        """(total, nseg, seg, idx, dst) device arrays of one push: segment s has counts[s] values for dst_ptrs[s]."""
+        import torch
+        seg = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), device=dev)
+        idx = None
+        if idx_list is not None:
+            idx = torch.cat(idx_list) if idx_list else torch.empty(0, dtype=torch.int32, device=dev)
+        dst = torch.tensor(list(dst_ptrs) or [0], dtype=torch.int64, device=dev)
+        return (int(sum(counts)), len(counts), seg, idx, dst)
+
+
+class PeerComm(_PeerKernels, SymmMemComm):
+    """One process per GPU; EVERY exchange of the iteration is a kernel storing into the peers' memory over NVLink:
+
+    * halo = pack-and-push fused with the barrier (``mwx_peer_push``: the last block to finish signals all peers'
+      epoch flags and waits for theirs) - one launch per exchange instead of push + symmetric-memory barrier;
+    * all-reduce of the CG scalars = ``mwx_peer_allreduce`` (every rank stores its partials into all peers' slots,
+      barrier, sum in rank order: deterministic, ~one NVLink round trip instead of an NCCL launch);
+    * all-gather of the coarse residual for the replicated tail = the same push kernel with one segment per rank.
+
+    No NCCL call and no host-side state is left inside an iteration, which is what lets ``dist_pcg`` capture it in
+    a CUDA graph.  NCCL (the parent classes) still does the setup-time exchanges."""
+
+    def __init__(self, group=None):
+        super().__init__(group)
+        import torch
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self._wait = 1
+        ctl = self._ctl_alloc(lambda n: self.symm_mem.empty(n, dtype=torch.float64, device=dev))
+        ctl.zero_()
+        hdl = self.symm_mem.rendezvous(ctl, self.group_name)
+        self._ctl = {self.rank: ctl}
+        self._ctl_hdl = hdl
+        self._peer_table = torch.tensor([int(hdl.buffer_ptrs[r]) for r in range(self.world)], dtype=torch.int64, device=dev)
+        self._gather_bufs = {}
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)           # every control block is zeroed before anyone signals
+
+    def _push_plan(self, p, v, hdl):
+        key = (id(p), v.data_ptr())
+        plan = self._plans.get(key)
+        if plan is None:
+            peers = [peer for peer in p.send if p.send[peer].numel()]
+            arrays = self._push_arrays([p.send[peer].numel() for peer in peers], [p.send[peer] for peer in peers],
+                                       [hdl.buffer_ptrs[peer] + 8 * p.push[peer] for peer in peers], v.device)
+            plan = self._plans[key] = (arrays, (p, v))
+        return plan[0]
+
+    def _guard(self, ptr_):
+        """A buffer the peers write into may only be overwritten after a synchronisation that follows its readers."""
+        if self.last_halo.get(ptr_) == self.epoch:
+            self._launch_barrier(self.rank)
+            self.epoch += 1
+
+    def halo(self, parts, vecs):
+        (p,), (v,) = parts, vecs
+        vp_ = v.data_ptr()
+        hdl, _base = self.handles[vp_]
+        self._guard(vp_)
+        self._launch_push(self.rank, self._push_plan(p, v, hdl), v, self._wait)
+        self.epoch += 1
+        self.last_halo[vp_] = self.epoch
+
+    def allreduce_sum(self, tensors):
+        (t,) = tensors
+        import torch
+        if t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 1 <= t.numel() <= 8:
+            self._launch_allreduce(self.rank, t, 0)
+            self.epoch += 1
+        else:
+            super().allreduce_sum(tensors)
+
+    def allgather(self, vecs, offsets):
+        import torch
+        (v,) = vecs
+        key = tuple(offsets)
+        ent = self._gather_bufs.get(key)
+        if ent is None:
+            full = self.symm_mem.empty(max(int(offsets[-1]), 1), dtype=torch.float64, device=v.device)
+            full.zero_()
+            hdl = self.symm_mem.rendezvous(full, self.group_name)
+            n = offsets[self.rank + 1] - offsets[self.rank]
+            arrays = self._push_arrays([n] * self.world, None,
+                                       [hdl.buffer_ptrs[r] + 8 * offsets[self.rank] for r in range(self.world)], v.device)
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            ent = self._gather_bufs[key] = (full, hdl, arrays)
+        full, _hdl, arrays = ent
+        self._guard(full.data_ptr())
+        self._launch_push(self.rank, arrays, v, self._wait)
+        self.epoch += 1
+        self.last_halo[full.data_ptr()] = self.epoch
+        return [full[:offsets[-1]]]
+
+
+class InProcessPeerComm(_PeerKernels, InProcessComm):
+    """All P parts in this process on one GPU, exchanged with the SAME peer kernels as :class:`PeerComm` (signal-only
+    barriers: one stream already orders the parts).  Checks the push / all-reduce / all-gather kernels and the
+    graph-captured iteration without a second GPU."""
+
+    def __init__(self, nparts):
+        super().__init__(nparts)
+        torch = L.require_cuda()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self._wait = 0
+        self._ctl = {r: self._ctl_alloc(lambda n: torch.zeros(n, dtype=torch.float64, device=dev)) for r in range(nparts)}
+        self._peer_table = torch.tensor([self._ctl[r].data_ptr() for r in range(nparts)], dtype=torch.int64, device=dev)
+        self._plans, self._gather_bufs = {}, {}
+
+    def halo(self, parts, vecs):
+        by_rank = {p.rank: (p, v) for p, v in zip(parts, vecs)}
+        for p, v in zip(parts, vecs):
+            key = (id(p), v.data_ptr()) + tuple(by_rank[q][1].data_ptr() for q in sorted(p.send))
+            plan = self._plans.get(key)
+            if plan is None:
+                peers = [q for q in sorted(p.send) if p.send[q].numel()]
+                dst = [by_rank[q][1].data_ptr() + 8 * (by_rank[q][0].ncol + by_rank[q][0].recv[p.rank][0]) for q in peers]
+                plan = self._plans[key] = (self._push_arrays([p.send[q].numel() for q in peers],
+                                                             [p.send[q] for q in peers], dst, v.device), (p, v))
+            self._launch_push(p.rank, plan[0], v, 0)
+
+    def allreduce_sum(self, tensors):
+        import torch
+        ok = len(tensors) == self.world and all(t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and
+                                                1 <= t.numel() <= 8 for t in tensors)
+        if not ok:
+            return super().allreduce_sum(tensors)
+        for r, t in enumerate(tensors):
+            self._launch_allreduce(r, t, 1)
+        for r, t in enumerate(tensors):
+            self._launch_allreduce(r, t, 2)
+
+    def allgather(self, vecs, offsets):
+        import torch
+        key = tuple(offsets)
+        ent = self._gather_bufs.get(key)
+        if ent is None:
+            fulls = [torch.zeros(max(int(offsets[-1]), 1), dtype=torch.float64, device=v.device) for v in vecs]
+            plans = [self._push_arrays([offsets[r + 1] - offsets[r]] * self.world, None,
+                                       [f.data_ptr() + 8 * offsets[r] for f in fulls], vecs[0].device)
+                     for r in range(self.world)]
+            ent = self._gather_bufs[key] = (fulls, plans)
+        fulls, plans = ent
+        for r, v in enumerate(vecs):
+            self._launch_push(r, plans[r], v, 0)
+        return [f[:offsets[-1]] for f in fulls]
+
+
 # ------------------------------------------------------------------------------------------ kernels behind the driver
 class CudaOps:
     """The device kernels (C ABI) the partitioned CG chains; tests substitute a CPU stand-in under gloo.
@@ -505,10 +701,15 @@ class CudaOps:
                    L.ptr(x_ext), L.ptr(b), L.ptr(r), L.ptr(dinv), L.ptr(ws), L.stream())
 
     def spmv(self, p, x_ext, y):
+        if getattr(p, 'bsr', None):
+            return self._emit('mwx_bsr_spmv', L.lib().mwx_bsr_spmv, p.bsr, L.ptr(x_ext), L.ptr(y), L.stream())
         self._emit('mwx_spmv', L.lib().mwx_spmv, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals),
                    L.ptr(x_ext), L.ptr(y), L.stream())
 
     def spmv_axpy(self, p, x_ext, c, sign, y):
+        if getattr(p, 'bsr', None):
+            return self._emit('mwx_bsr_spmv_axpy', L.lib().mwx_bsr_spmv_axpy, p.bsr, L.ptr(x_ext), L.ptr(c), int(sign),
+                              L.ptr(y), L.stream())
         self._emit('mwx_spmv_axpy', L.lib().mwx_spmv_axpy, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
 
@@ -517,6 +718,9 @@ class CudaOps:
                    L.ptr(d), L.stream())
 
     def smoother_step(self, p, x_in, x_out, b, dinv, d, c1, c2):
+        if getattr(p, 'bsr', None):
+            return self._emit('mwx_bsr_smoother_step', L.lib().mwx_bsr_smoother_step, p.bsr, L.ptr(x_in), L.ptr(x_out),
+                              L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2), L.stream())
         self._emit('mwx_smoother_step', L.lib().mwx_smoother_step, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2),
                    L.stream())
@@ -674,11 +878,28 @@ def dist_pcg(parts, comm, b_list, tol=1e-8, maxiter=None, precond='jacobi', amg=
         return None
     verdict.last = resid
 
+    # With a communicator whose exchanges are all kernels (PeerComm / InProcessPeerComm: `graphable`) iterations 2..
+    # are ONE CUDA-graph launch each: the iteration (xp copy, V-cycle with its halos, CG kernels, all-reduces) is
+    # captured once per cached solver state and replayed - no per-launch host work is left on the critical path.
+    use_graph = on_gpu and getattr(comm, 'graphable', False) and os.environ.get('MWX_DIST_GRAPH', '1') != '0'
+
+    def later_iteration():
+        for p, st in zip(parts, S):
+            st['xp'][:p.nloc].copy_(st['x'][:p.nloc])            # iterate of the previous iteration
+        iteration(False)
+
     for it in range(1, maxiter + 1):
-        if it > 1:
-            for p, st in zip(parts, S):
-                st['xp'][:p.nloc].copy_(st['x'][:p.nloc])        # iterate of iteration it - 1
-        iteration(it == 1)
+        if it == 1:
+            iteration(True)
+        elif use_graph:
+            if cache.get('graph') is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    later_iteration()
+                cache['graph'] = g
+            cache['graph'].replay()
+        else:
+            later_iteration()
         post(it)
         if it > 1:
             # NOTE: the re-check's residual kernel and all-reduce run AFTER iteration `it` was queued; they only
@@ -813,9 +1034,13 @@ class DistAMG:
             lv = dict(A=[], P=[], R=[])
             for p in parts:
                 r = p.rank
-                lv['A'].append(p if l == 0 else LocalOp(*A_full, offs[l][r], offs[l][r + 1], offs[l], r))
-                lv['P'].append(LocalOp(*P_full, offs[l][r], offs[l][r + 1], offs[l + 1], r))
-                lv['R'].append(LocalOp(*R_full, offs[l + 1][r], offs[l + 1][r + 1], offs[l], r))
+                # mode 'sa' on three candidates: every operator below the fine matrix comes in 3-wide blocks (bsr.cu)
+                wide = 3 if mode == 'sa' else None
+                blk = (lambda br, bc: (br, bc)) if wide else (lambda br, bc: None)
+                fine = 1 if l == 0 else wide
+                lv['A'].append(p if l == 0 else LocalOp(*A_full, offs[l][r], offs[l][r + 1], offs[l], r, block=blk(wide, wide)))
+                lv['P'].append(LocalOp(*P_full, offs[l][r], offs[l][r + 1], offs[l + 1], r, block=blk(fine, wide)))
+                lv['R'].append(LocalOp(*R_full, offs[l + 1][r], offs[l + 1][r + 1], offs[l], r, block=blk(wide, fine)))
             for key in ('A', 'P', 'R'):
                 if not (key == 'A' and l == 0):
                     comm.exchange_requests(lv[key])
@@ -1001,6 +1226,9 @@ class DistAMG:
         """z = M^-1 r (collective).  The cycle is traced once per set of input buffers into a list of
         (kernel, prebuilt arguments) / host-step entries and replayed afterwards."""
         if not hasattr(self.ops, 'record') or os.environ.get('MWX_DIST_REPLAY', '1') == '0':   # stand-in ops / A-B switch
+            return self._cycle(0, r_list)
+        torch = L.require_cuda()
+        if torch.cuda.is_current_stream_capturing():            # graph capture: launch on the capturing stream
             return self._cycle(0, r_list)
         key = tuple(r.data_ptr() for r in r_list)
         if key not in self._programs:

@@ -156,7 +156,12 @@ class AMGHierarchy:
         if setup not in ('host', 'device') or (setup == 'device' and not sa):
             raise ValueError("setup='device' is the smoothed-aggregation setup (mode='sa')")
         theta = (0.1 if sa else 0.25) if theta is None else theta
-        max_coarse = (300 if sa else 10) if max_coarse is None else max_coarse
+        if max_coarse is None:
+            # 'sa': the last levels of an aggregation hierarchy are small but nearly dense - a few thousand rows cost
+            # 30-100 us per kernel (latency-bound) and a gamma = 2 cycle visits them 8 times per iteration, so the
+            # hierarchy stops at <= 4000 rows and that level is solved by one dense GEMV with its inverse
+            import os
+            max_coarse = int(os.environ.get('MWX_SA_MAX_COARSE', 4000)) if sa else 10
         lib = L.lib()
         A = _to_device_csr(A)
         self.n, self.mode, self.setup = A.shape[0], mode, setup
@@ -199,8 +204,7 @@ class AMGHierarchy:
             self.levels = lib.mwx_amg_dev_num_levels(self._dev)
             if upload:                      # upload=False: operators only (the partitioned solver slices them itself)
                 self._check_coarsest()
-                Ac = self.level_matrix(self.levels - 1, 0).toarray()
-                pinv = self._pinv2(Ac)
+                pinv = self._pinv_coarse(self.level_matrix(self.levels - 1, 0).toarray())
                 L.check(lib.mwx_amg_dev_finalize(self._dev, L.ptr(pinv), L.stream()), 'mwx_amg_dev_finalize')
                 self._default_cycle()
             torch.cuda.synchronize()
@@ -229,7 +233,8 @@ class AMGHierarchy:
         t1 = time.perf_counter()
         # coarsest level: dense pseudo-inverse (scipy 1.4.1 pinv2 semantics) through LAPACK
         self._check_coarsest()
-        pinv = self._pinv2(self.level_matrix(self.levels - 1, 0).toarray())
+        Ac = self.level_matrix(self.levels - 1, 0).toarray()
+        pinv = self._pinv_coarse(Ac) if sa else self._pinv2(Ac)
         self._dev = ctypes.c_void_p()
         L.check(lib.mwx_amg_upload(self._host, self.MODES[mode], int(degree), L.ptr(pinv),
                                    ctypes.byref(self._dev), L.stream()), 'mwx_amg_upload')
@@ -262,6 +267,28 @@ class AMGHierarchy:
         u, s, vh = np.linalg.svd(Ac, full_matrices=False)
         rank = int(np.sum(s > 1e6 * np.finfo(np.float64).eps * s.max())) if s.size else 0
         return np.ascontiguousarray(((u[:, :rank] / s[:rank]) @ vh[:rank]).T)
+
+    @classmethod
+    def _pinv_coarse(cls, Ac):
+        """Inverse of the coarsest operator of a smoothed-aggregation hierarchy (symmetric positive definite: Galerkin
+        products of an SPD matrix with full-rank prolongators, unit diagonal for dead coarse DOFs).  Up to 300 rows: the
+        SVD of ``_pinv2``; larger: Cholesky on the device (setup only), symmetric eigendecomposition with ``_pinv2``'s
+        relative cutoff if the factorisation breaks down."""
+        n = Ac.shape[0]
+        if n <= 300:
+            return cls._pinv2(Ac)
+        torch = L.require_cuda()
+        Ad = torch.from_numpy(np.ascontiguousarray(Ac, dtype=np.float64)).cuda()
+        Ad = 0.5 * (Ad + Ad.T)
+        Lc, info = torch.linalg.cholesky_ex(Ad)
+        if int(info.item()) == 0:
+            inv = torch.cholesky_inverse(Lc)
+            if bool(torch.isfinite(inv).all()):
+                return np.ascontiguousarray((0.5 * (inv + inv.T)).cpu().numpy())
+        w, V = torch.linalg.eigh(Ad)
+        keep = w.abs() > 1e6 * np.finfo(np.float64).eps * w.abs().max()
+        winv = torch.where(keep, 1.0 / torch.where(keep, w, torch.ones_like(w)), torch.zeros_like(w))
+        return np.ascontiguousarray(((V * winv) @ V.T).cpu().numpy())
 
     def set_chebyshev(self, degree=2, ratio=10.0):
         L.check(L.lib().mwx_amg_set_chebyshev(self._dev, int(degree), float(ratio)), 'mwx_amg_set_chebyshev')

@@ -398,6 +398,35 @@ int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *idx, double 
 int mwx_halo_push(int64_t total, int32_t nseg, const int64_t *seg, const int32_t *idx, const double *v,
                   double *const *dst, void *stream);
 
+/* Block-CSR twin of a CSR operator whose nonzeros come in br x bc blocks (3x3, 1x3, 3x1: the coarse operators of a
+ * smoothed-aggregation hierarchy on three candidates); *out = NULL (status 0) when the operator is not blocked that way.
+ * Used for the row blocks of the partitioned V-cycle; inside a single-GPU hierarchy the library builds them itself. */
+int mwx_bsr_create(int64_t rows, int64_t cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                   const double *values, int32_t br, int32_t bc, void **out, void *stream);
+void mwx_bsr_destroy(void *bsr);
+int mwx_bsr_spmv(const void *bsr, const double *x, double *y, void *stream);                       /* y = A x */
+int mwx_bsr_spmv_axpy(const void *bsr, const double *x, const double *c, int32_t sign, double *y,
+                      void *stream);                                                               /* y = c +- A x */
+int mwx_bsr_smoother_step(const void *bsr, const double *x_in, double *x_out, const double *rhs, const double *dinv,
+                          double *d, double c1, double c2, void *stream);   /* as mwx_smoother_step */
+
+/* Peer-memory collectives of the partitioned iteration (one process per GPU; NVLink / NVSwitch peer mappings).
+ * ctl: this rank's control block (mwx_peer_ctl_bytes() bytes, zero-initialised, in memory every peer has mapped);
+ * peers: device array of `world` pointers to the ranks' control blocks.  The barrier epoch is device-resident, so
+ * these launches can be captured in a CUDA graph and replayed (the whole PCG iteration is one graph launch).
+ * wait = 1: full barrier; 0: signal only (all parts in one process on one stream - tests). */
+int mwx_peer_ctl_bytes(void);
+int mwx_peer_barrier(void *ctl, const void *peers, int32_t rank, int32_t world, int32_t wait, void *stream);
+/* Halo push / all-gather fused with the barrier: dst[s][i - seg[s]] = v[idx ? idx[i] : i - seg[s]], then the last
+ * block to finish signals the peers and waits for them; when the launch retires every rank's values have landed. */
+int mwx_peer_push(int64_t total, int32_t nseg, const int64_t *seg, const int32_t *idx, const double *v,
+                  double *const *dst, void *ctl, const void *peers, int32_t rank, int32_t world, int32_t wait,
+                  void *stream);
+/* vals[0..count) (count <= 8) <- sum over the ranks, added in rank order (bitwise identical on every rank).
+ * phase 0: the whole all-reduce; 1 / 2: its write / sum half (in-process parts). */
+int mwx_peer_allreduce(double *vals, int32_t count, void *ctl, const void *peers, int32_t rank, int32_t world,
+                       int32_t phase, void *stream);
+
 /* CG building blocks chained by the multi-GPU driver between halo exchanges and all-reduces.  ws: zero-initialised
  * workspace of mwx_dcg_workspace_doubles() doubles; ws[0..4] = {rho, rho_prev, pq, rr, aux}.  Kernels leave LOCAL
  * partial sums there (deterministic per rank); the driver all-reduces them.  x_ext = [owned | ghost] vector. */

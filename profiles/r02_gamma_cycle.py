@@ -8,7 +8,8 @@ from profiles.r02_sa_setup_probe_lib import system
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 11
 Kc, bc = system(level)
 ml = F.AMGHierarchy(Kc, mode='sa')
-for gamma, k0, k in ((1, 1, 0), (2, 1, 9), (2, 2, 9), (2, 2, 3), (2, 2, 4), (2, 1, 4), (2, 3, 9)):
+print(json.dumps(dict(levels=ml.level_sizes(), max_coarse=os.environ.get('MWX_SA_MAX_COARSE'), setup_s=ml.setup_device_seconds)), flush=True)
+for gamma, k0, k in ((1, 1, 0), (2, 2, 2), (2, 2, 3), (2, 2, 4), (2, 2, 9), (2, 3, 4), (2, 3, 3)):
     ml.set_cycle(gamma, k, first=k0)
     F.pcg(Kc, bc, tol=1e-8, amg=ml, max_rechecks=3)
     torch.cuda.synchronize(); t = time.perf_counter()

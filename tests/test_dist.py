@@ -127,7 +127,7 @@ def test_rcb_partition_is_balanced_and_compact():
 
 
 # ------------------------------------------------------------------ GPU
-def _setup(level, nparts, eps2=1e-4):
+def _setup(level, nparts, eps2=1e-4, peer=False):
     import fem_forth_perturb_b200 as F
     from fem_forth_perturb_b200 import dist as D
     gm = F.MeshTri().refine(level)
@@ -135,7 +135,7 @@ def _setup(level, nparts, eps2=1e-4):
     bf = gm.boundary_facets()
     Dset = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
     form = eps2 * F.a_load + F.b_load
-    prob = D.PartitionedProblem(basis, Dset, D.InProcessComm(nparts)).assemble(form)
+    prob = D.PartitionedProblem(basis, Dset, (D.InProcessPeerComm if peer else D.InProcessComm)(nparts)).assemble(form)
     K2 = F.asm_gpu(form, basis)
     Kc = F.condense(K2, D=Dset, expand=False)
     return F, D, prob, Kc
@@ -160,11 +160,12 @@ def test_partitioned_operator_equals_permuted_global(cuda, nparts):
 
 
 @pytest.mark.gpu
-def test_partitioned_pcg_independent_of_partition_count(cuda):
+@pytest.mark.parametrize('peer', [False, True])
+def test_partitioned_pcg_independent_of_partition_count(cuda, peer):
     torch = cuda
     its_seen = {}
     for nparts in (1, 2, 4):
-        F, D, prob, Kc = _setup(5, nparts, eps2=1e-4)
+        F, D, prob, Kc = _setup(5, nparts, eps2=1e-4, peer=peer)
         rng = np.random.default_rng(3)
         b_old = rng.standard_normal(Kc.shape[0])
         perm = prob.partition.perm.cpu().numpy()
@@ -190,15 +191,17 @@ def test_partitioned_pcg_independent_of_partition_count(cuda):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('peer', [False, True])
 @pytest.mark.parametrize('min_rows,switch_rows', [(10000, 600), (50, 100), (50, 600), (50, 3000)])
-def test_distributed_smoothed_aggregation_matches_single_gpu(cuda, monkeypatch, min_rows, switch_rows):
+def test_distributed_smoothed_aggregation_matches_single_gpu(cuda, monkeypatch, min_rows, switch_rows, peer):
     """mode='sa' through the partitioned V-cycle: aggregates are numbered by seed, so coarse levels stay row-blocked.
     min_rows = 50 turns the gamma = 2 revisit of level 2 on at this problem size: with that level row-blocked
     (switch_rows 100), as the first replicated level (600: revisited inside the tail step) and as a level inside the
     replicated tail hierarchy (3000)."""
     torch = cuda
     monkeypatch.setenv('MWX_SA_CYCLE_MIN_ROWS', str(min_rows))
-    F, D, prob, Kc = _setup(6, 3, eps2=0.25)
+    monkeypatch.setenv('MWX_SA_MAX_COARSE', '300')          # keep a deep hierarchy at this small size (default: stop at <= 4000 rows)
+    F, D, prob, Kc = _setup(6, 3, eps2=0.25, peer=peer)
     from fem_forth_perturb_b200.solvers import Reordering, _run_pcg
     ro = Reordering.for_matrix(Kc)
     ro.perm, ro.iperm = prob.partition.perm, prob.partition.iperm
@@ -217,14 +220,27 @@ def test_distributed_smoothed_aggregation_matches_single_gpu(cuda, monkeypatch, 
     x1, its1, info1, _ = _run_pcg(Kp, b_new, 1e-8, None, amg=single, reordering=None)
     assert info == 0 and info1 == 0 and abs(its - its1) <= 1
     assert float(torch.linalg.norm(torch.cat(xs) - x1) / torch.linalg.norm(x1)) < 1e-6
+    if peer:
+        # peer kernels: iterations 2.. are replays of ONE captured CUDA graph; a second solve (other right-hand side)
+        # reuses it, and the eager path (MWX_DIST_GRAPH=0) gives the same iterates
+        assert prob.parts[0]._cg_state.get('graph') is not None
+        b2 = torch.from_numpy(rng.standard_normal(Kc.shape[0])).cuda()
+        xs2, its2, info2, _ = D.dist_pcg(prob.parts, prob.comm, [b2[p.lo:p.hi].clone() for p in prob.parts], tol=1e-8,
+                                         precond='amg', amg=amg)
+        monkeypatch.setenv('MWX_DIST_GRAPH', '0')
+        xs3, its3, info3, _ = D.dist_pcg(prob.parts, prob.comm, [b2[p.lo:p.hi].clone() for p in prob.parts], tol=1e-8,
+                                         precond='amg', amg=amg)
+        assert info2 == 0 and info3 == 0 and its2 == its3
+        assert float(torch.linalg.norm(torch.cat(xs2) - torch.cat(xs3)) / torch.linalg.norm(torch.cat(xs3))) < 1e-12
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('peer', [False, True])
 @pytest.mark.parametrize('nparts', [1, 2, 4])
-def test_distributed_vcycle_matches_single_gpu_fast_mode(cuda, nparts):
+def test_distributed_vcycle_matches_single_gpu_fast_mode(cuda, nparts, peer):
     """Global hierarchy applied as a collective V-cycle: same iteration count as the single-GPU fast mode."""
     torch = cuda
-    F, D, prob, Kc = _setup(6, nparts, eps2=1e-4)
+    F, D, prob, Kc = _setup(6, nparts, eps2=1e-4, peer=peer)
     from fem_forth_perturb_b200.solvers import Reordering
     ro = Reordering.for_matrix(Kc)
     ro.perm, ro.iperm = prob.partition.perm, prob.partition.iperm          # the partition's numbering
@@ -262,7 +278,7 @@ basis = F.InteriorBasis(gm, F.ElementTriMorley())
 bf = gm.boundary_facets()
 Dset = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
 form = 1e-4 * F.a_load + F.b_load
-comm = D.SymmMemComm() if os.environ.get("MWX_TEST_HALO") == "peer" else D.TorchDistComm()
+comm = {"peer": D.PeerComm, "symm": D.SymmMemComm, "nccl": D.TorchDistComm}[os.environ["MWX_TEST_HALO"]]()
 prob = D.PartitionedProblem(basis, Dset, comm).assemble(form)
 (p,) = prob.parts
 Kc = F.condense(F.asm_gpu(form, basis), D=Dset, expand=False)
@@ -283,15 +299,23 @@ single = F.AMGHierarchy(Kp, mode="chebyshev", reorder=False)
 x1, it1, info1, _ = _run_pcg(Kp, b_new, 1e-8, None, amg=single)
 assert info == 0 and abs(its_a - it1) <= 1, (its_a, it1)
 assert float(torch.linalg.norm(xs[0] - x1[p.lo:p.hi]) / torch.linalg.norm(x1)) < 1e-7
+if os.environ["MWX_TEST_HALO"] == "peer":          # graph-captured iteration: replayed by a second solve, equal to the eager path
+    assert prob.parts[0]._cg_state.get("graph") is not None
+    xs2, its2, info2, _ = D.dist_pcg(prob.parts, comm, [b_new[p.lo:p.hi].clone()], tol=1e-8, precond="amg", amg=amg)
+    os.environ["MWX_DIST_GRAPH"] = "0"
+    xs3, its3, info3, _ = D.dist_pcg(prob.parts, comm, [b_new[p.lo:p.hi].clone()], tol=1e-8, precond="amg", amg=amg)
+    assert info2 == 0 and info3 == 0 and its2 == its_a and its3 == its_a, (its_a, its2, its3)
+    assert float(torch.linalg.norm(xs2[0] - xs3[0])) <= 1e-12 * float(torch.linalg.norm(xs3[0]))
 sys.stdout.write(f"RANK{dist.get_rank()}-OK its={its} ref={it_ref} amg={its_a}\n"); sys.stdout.flush()
 dist.destroy_process_group()
 '''
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('halo', ['nccl', 'peer'])
+@pytest.mark.parametrize('halo', ['nccl', 'symm', 'peer'])
 def test_partitioned_pcg_two_gpus(cuda, tmp_path, halo):
-    """halo = NCCL send/recv, or pack-and-push kernels into the neighbour's peer memory (symmetric memory)."""
+    """halo = NCCL send/recv; pack-and-push kernels into the neighbour's peer memory + symmetric-memory barrier ('symm');
+    or every exchange (halo, all-reduce, all-gather) as peer kernels with the iteration captured in a CUDA graph ('peer')."""
     if cuda.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
     script = tmp_path / 'worker_gpu.py'

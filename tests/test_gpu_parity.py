@@ -495,10 +495,11 @@ def test_amg_fast_modes_converge_to_the_same_solution(cuda, mode):
     assert np.linalg.norm(x - x_d) <= 1e-10 * np.linalg.norm(x_d)
 
 
-def test_smoothed_aggregation_mode(cuda):
+def test_smoothed_aggregation_mode(cuda, monkeypatch):
     """mode='sa' (throughput): same solution as the reference hierarchy, far fewer iterations where the fourth-order
     term dominates; candidates travel with the matrix through condense and the solver's renumbering."""
     import fem_forth_perturb_b200 as F
+    monkeypatch.setenv('MWX_SA_MAX_COARSE', '300')          # a deep hierarchy at this small size (default: stop at <= 4000 rows)
     gm = F.MeshTri().refine(6)
     basis = F.InteriorBasis(gm, F.ElementTriMorley())
     K = F.asm_gpu(0.25 * F.a_load + F.b_load, basis)
@@ -527,13 +528,20 @@ def test_smoothed_aggregation_mode(cuda):
         F.AMGHierarchy(F.DeviceCSR.from_scipy(Kc.tocsr()), mode='sa')          # no candidates attached
     ml2 = F.AMGHierarchy(F.DeviceCSR.from_scipy(Kc.tocsr()), mode='sa', candidates=B[I])
     assert ml2.level_sizes() == F.AMGHierarchy(Kc, mode='sa', reorder=False).level_sizes()
+    # default coarsest level: up to 4000 rows, solved by one dense GEMV with the Cholesky inverse (built on the device)
+    monkeypatch.delenv('MWX_SA_MAX_COARSE')
+    ml3 = F.AMGHierarchy(Kc, mode='sa')
+    assert ml3.levels < ml.levels and 300 < ml3.level_sizes()[-1] <= 4000
+    x3, it3, info3, _ = F.pcg(Kc, bc, tol=1e-10, amg=ml3)
+    assert info3 == 0 and it3 <= its['sa'] + 1 and np.linalg.norm(x3.cpu().numpy() - x_d) <= 1e-8 * np.linalg.norm(x_d)
 
 
-def test_smoothed_aggregation_device_setup(cuda):
+def test_smoothed_aggregation_device_setup(cuda, monkeypatch):
     """mode='sa' builds its hierarchy on the device by default (csrc/amg_setup_dev.cu).  Checked against sparse algebra
     on the host: R = P^T exactly, A_c = R A P, the smoothed prolongator reproduces the candidates (P B_c = (I - w D^-1 A) B),
     aggregates cover every node; the setup is bit-reproducible; the solve matches the host-built hierarchy's."""
     import fem_forth_perturb_b200 as F
+    monkeypatch.setenv('MWX_SA_MAX_COARSE', '300')
     gm = F.MeshTri().refine(6)
     basis = F.InteriorBasis(gm, F.ElementTriMorley())
     K = F.asm_gpu(1e-4 * F.a_load + F.b_load, basis)
@@ -594,6 +602,7 @@ def test_block_csr_kernels_match_the_scalar_spmv(cuda, monkeypatch):
     D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
     Kc = F.condense(K, D=D, expand=False)
     r = torch.from_numpy(np.random.default_rng(8).standard_normal(Kc.shape[0])).cuda()
+    monkeypatch.setenv('MWX_SA_MAX_COARSE', '300')
     monkeypatch.setenv('MWX_BSR', '1')
     ml_b = F.AMGHierarchy(Kc, mode='sa')
     monkeypatch.setenv('MWX_BSR', '0')
