@@ -477,6 +477,8 @@ def run_single(args, torch, F, L, dev, local):
                 'amg_device_setup_s': ml.setup_device_seconds, 'amg_upload_s': ml.upload_seconds,
                 'amg_reorder_s': ml.reorder_seconds, 'levels': ml.level_sizes(),
                 'operator_complexity': ml.operator_complexity(),
+                'hierarchy_storage': ('operator values in fp32 (8-byte packed CSR records / fp32 block-CSR planes), vectors, products and sums '
+                                      'in fp64; the system matrix CG multiplies with stays fp64' if getattr(ml, 'storage_bits', 64) == 32 else 'fp64'),
                 'rel_err_vs_manufactured': float(torch.linalg.norm(rr[-1]['x'] - xstar) / torch.linalg.norm(xstar))}
 
     by_mode = {args.mode: mode_block(args.mode, ms_step, e2e_ms / args.steps, rs)}
@@ -895,6 +897,7 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
                 'rel_err_vs_manufactured': float(torch.sqrt(err2[0] / err2[1])),
                 'level_offsets': [o[-1] for o in ml.offsets], 'distributed_levels': ml.lsw, 'levels': nlev,
                 'revisited_levels': list(getattr(ml, 'revisit', ())),
+                'hierarchy_storage_bits': getattr(ml, 'storage_bits', 64),
                 'block_csr_operators': sum(1 for lv in ml.levels for k in 'APR' for op in lv[k] if getattr(op, 'bsr', None)),
                 'cuda_graph': bool(getattr(comm, 'graphable', False)) and os.environ.get('MWX_DIST_GRAPH', '1') != '0'},
         'spmv': {'ms': float(phmax[1]), 'gbs_per_gpu': spmv_gbs_rank, 'frac_of_peak': spmv_gbs_rank / peak,

@@ -52,7 +52,12 @@ _SIGNATURES = {
     'mwx_dist_localize': [i64, vp, i32, i32, vp, i32, i32, vp, vp],
     'mwx_gather_f64_i64': [i64, vp, vp, vp, vp],
     'mwx_halo_push': [i64, i32, vp, vp, vp, vp, vp],
-    'mwx_bsr_create': [i64, i64, i64, vp, vp, vp, i32, i32, ctypes.POINTER(vp), vp],
+    'mwx_bsr_create': [i64, i64, i64, vp, vp, vp, i32, i32, i32, ctypes.POINTER(vp), vp],
+    'mwx_amg_set_storage': [vp, i32, vp],
+    'mwx_csr_pack': [i64, vp, vp, vp, vp],
+    'mwx_spmv_pk': [i64, i64, vp, vp, vp, vp, vp],
+    'mwx_spmv_axpy_pk': [i64, i64, vp, vp, vp, vp, i32, vp, vp],
+    'mwx_smoother_step_pk': [i64, i64, vp, vp, vp, vp, vp, vp, vp, f64, f64, vp],
     'mwx_bsr_destroy': [vp],
     'mwx_bsr_spmv': [vp, vp, vp, vp],
     'mwx_bsr_spmv_axpy': [vp, vp, vp, i32, vp, vp],

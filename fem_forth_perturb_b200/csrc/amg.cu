@@ -277,6 +277,7 @@ inline unsigned vgrid(int64_t n) {
 
 void free_csr(DCsr &m) {
     free_bsr(m.bsr);
+    cudaFree(m.pk);
     if (!m.borrowed) { cudaFree(m.ptr); cudaFree(m.idx); cudaFree(m.val); }
     m = DCsr();
 }
@@ -503,15 +504,18 @@ extern "C" int mwx_amg_upload(const mwx_amg_host_t *h, int32_t smoother, int32_t
 // Operator applications of the V-cycle: the block kernels where the operator has a block-CSR twin, else k_spmv.
 static int op_spmv(const DCsr &M, const double *x, double *y, cudaStream_t st) {
     if (M.bsr.bptr) return bsr_spmv(M.bsr, x, y, st);
+    if (M.pk) return launch_spmv_pk(M.rows, M.plan, M.ptr, M.pk, x, y, st);
     return launch_spmv(M.rows, M.plan, M.ptr, M.idx, M.val, x, y, nullptr, nullptr, nullptr, nullptr, st);
 }
 static int op_spmv_axpy(const DCsr &M, const double *x, double *y, const double *c, int sign, cudaStream_t st) {
     if (M.bsr.bptr) return bsr_spmv_axpy(M.bsr, x, y, c, sign, st);
+    if (M.pk) return launch_spmv_axpy_pk(M.rows, M.plan, M.ptr, M.pk, x, y, c, sign, st);
     return launch_spmv_axpy(M.rows, M.plan, M.ptr, M.idx, M.val, x, y, c, sign, st);
 }
 static int op_smoother_step(const DCsr &M, const double *x_in, double *x_out, const double *b, const double *dinv,
                             double *d, double c1, double c2, cudaStream_t st) {
     if (M.bsr.bptr) return bsr_smoother_step(M.bsr, x_in, x_out, b, dinv, d, c1, c2, st);
+    if (M.pk) return launch_smoother_step_pk(M.rows, M.plan, M.ptr, M.pk, x_in, x_out, b, dinv, d, c1, c2, st);
     return launch_smoother_step(M.rows, M.plan, M.ptr, M.idx, M.val, x_in, x_out, b, dinv, d, c1, c2, st);
 }
 
@@ -693,6 +697,38 @@ extern "C" int mwx_amg_set_chebyshev(mwx_amg_dev_t *d, int32_t degree, double ra
     if (!d || degree < 1 || degree > 16 || !(ratio > 1.0)) return MWX_E_BADARG;
     d->degree = degree;
     d->cheb_ratio = ratio;
+    return 0;
+}
+
+// Keep the operators the V-cycle applies in fp32 (values only): block-CSR planes are converted in place.  Scalar
+// operators (the fine matrix) stay fp64: their kernel is bound by the L1 wavefronts of the x gathers, not by DRAM, and
+// the packed (fp32 value, column) twin measured SLOWER (2.95 against 2.73 ms per smoother step at 67 M rows: one more
+// shared-memory read per record pair) - MWX_PACKED_CSR=1 builds those twins anyway (A/B runs, tests).  The fp64 CSR
+// arrays stay for the accessors; vectors, products and sums stay fp64.  Fast smoothers only (parity mode is the
+// reference's arithmetic).  bits = 64 is a no-op (the twins are not rebuilt in fp64).
+extern "C" int mwx_amg_set_storage(mwx_amg_dev_t *d, int32_t bits, void *stream) {
+    if (!d || (bits != 32 && bits != 64)) return MWX_E_BADARG;
+    if (bits == 64 || d->smoother == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    const int nl = (int)d->lv.size();
+    const char *pk_env = std::getenv("MWX_PACKED_CSR");
+    const bool packed_too = pk_env && std::atoi(pk_env) != 0;
+    for (int l = 0; l + 1 < nl; ++l) {
+        DLevel &L = d->lv[(size_t)l];
+        DCsr *ops[3] = {&L.A, &L.P, &L.R};
+        for (DCsr *M : ops) {
+            if (!M->ptr || M->nnz <= 0) continue;
+            int rc;
+            if (M->bsr.bptr) {
+                if ((rc = bsr_store_fp32(M->bsr, st))) return rc;
+            } else if (packed_too && !M->pk) {
+                if (cudaMalloc((void **)&M->pk, sizeof(PackedNz) * (size_t)M->nnz) != cudaSuccess) { M->pk = nullptr; return MWX_E_NOMEM; }
+                if ((rc = csr_pack(M->nnz, M->idx, M->val, M->pk, st))) return rc;
+            }
+        }
+    }
+    MWX_CUDA(cudaStreamSynchronize(st));
+    d->storage_bits = 32;
     return 0;
 }
 

@@ -14,6 +14,7 @@ struct DBsr {
     int64_t *bptr = nullptr;
     int32_t *bidx = nullptr;
     double *bval = nullptr;
+    float *bval32 = nullptr;                   // fp32-stored planes (then bval == nullptr), see bsr_store_fp32
 };
 
 struct DCsr {
@@ -24,6 +25,7 @@ struct DCsr {
     int32_t *idx = nullptr;
     double *val = nullptr;
     DBsr bsr;                                  // set (bptr != nullptr) when the V-cycle should use the block kernels
+    PackedNz *pk = nullptr;                    // fp32-stored twin of a scalar operator (krylov.cuh), used instead of idx/val
 };
 
 // One direction of the exact lexicographic Gauss-Seidel sweep, level-scheduled: rows grouped by dependency wavefront,
@@ -57,6 +59,7 @@ struct DLevel {
 void free_csr(DCsr &m);
 void free_bsr(DBsr &B);
 int bsr_from_csr(const DCsr &A, int br, int bc, DBsr &out, cudaStream_t st);
+int bsr_store_fp32(DBsr &B, cudaStream_t st);
 int bsr_spmv(const DBsr &B, const double *x, double *y, cudaStream_t st);
 int bsr_spmv_axpy(const DBsr &B, const double *x, double *y, const double *c, int sign, cudaStream_t st);
 int bsr_smoother_step(const DBsr &B, const double *x_in, double *x_out, const double *b, const double *dinv, double *d,
@@ -73,6 +76,7 @@ struct mwx_amg_dev {
     int64_t n_last = 0;
     int smoother = 0, degree = 2;
     double cheb_ratio = 10.0;
+    int storage_bits = 64;               // 32: the V-cycle's operators are stored in fp32 (mwx_amg_set_storage)
     int gamma = 1, gamma_first = 1, gamma_last = 0;    // gamma = 2: levels gamma_first .. gamma_last are visited twice per visit of their parent
     mwx::CgScalars *sc = nullptr;
     double *partials = nullptr;

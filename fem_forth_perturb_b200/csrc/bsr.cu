@@ -35,9 +35,9 @@ __device__ __forceinline__ void bsr_finish(int64_t r, double sum, const double *
     y[r] = sum;
 }
 
-template <int BC, int MODE>
+template <typename VT, int BC, int MODE>
 __global__ void __launch_bounds__(256) k_bsr_rows3(int64_t nbrows, int64_t nblocks, const int64_t *__restrict__ bptr,
-                                                   const int32_t *__restrict__ bidx, const double *__restrict__ bval,
+                                                   const int32_t *__restrict__ bidx, const VT *__restrict__ bval,
                                                    const double *__restrict__ x, double *y, const double *cvec,
                                                    BsrSmoother sm, int lpr) {
     const int sub = threadIdx.x & (lpr - 1);
@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(256) k_bsr_rows3(int64_t nbrows, int64_t nbloc
                 double v[2][3 * BC], xv[2][BC];
 #pragma unroll
                 for (int k = 0; k < 3 * BC; ++k) {
-                    v[0][k] = bval[(int64_t)k * nblocks + b];
-                    v[1][k] = two ? bval[(int64_t)k * nblocks + bb] : 0.0;
+                    v[0][k] = (double)bval[(int64_t)k * nblocks + b];
+                    v[1][k] = two ? (double)bval[(int64_t)k * nblocks + bb] : 0.0;
                 }
 #pragma unroll
                 for (int c = 0; c < BC; ++c) { xv[0][c] = __ldg(x + j0 + c); xv[1][c] = __ldg(x + j1 + c); }
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(256) k_bsr_rows3(int64_t nbrows, int64_t nbloc
     }
 }
 
-template <int MODE>
+template <typename VT, int MODE>
 __global__ void __launch_bounds__(256) k_bsr_rows1(int64_t nrows, int64_t nblocks, const int64_t *__restrict__ bptr,
-                                                   const int32_t *__restrict__ bidx, const double *__restrict__ bval,
+                                                   const int32_t *__restrict__ bidx, const VT *__restrict__ bval,
                                                    const double *__restrict__ x, double *y, const double *cvec,
                                                    BsrSmoother sm) {
     const int64_t st = (int64_t)gridDim.x * blockDim.x;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) k_bsr_rows1(int64_t nrows, int64_t nblock
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v[u][k] = j[u] >= 0 ? bval[(int64_t)k * nblocks + b + u] : 0.0;
+                for (int k = 0; k < 3; ++k) v[u][k] = j[u] >= 0 ? (double)bval[(int64_t)k * nblocks + b + u] : 0.0;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -161,27 +161,51 @@ inline unsigned bsr_grid(int64_t threads_wanted) {
     return (unsigned)(g < 1 ? 1 : g);
 }
 
-template <int MODE>
-int bsr_launch(const DBsr &B, const double *x, double *y, const double *c, BsrSmoother sm, cudaStream_t st) {
+template <typename VT, int MODE>
+int bsr_launch_t(const DBsr &B, const VT *bval, const double *x, double *y, const double *c, BsrSmoother sm, cudaStream_t st) {
     if (B.br == 3) {
         const int lpr = B.lanes;
         const unsigned grid = bsr_grid(B.nbrows * lpr);
         if (B.bc == 3)
-            k_bsr_rows3<3, MODE><<<grid, 256, 0, st>>>(B.nbrows, B.nblocks, B.bptr, B.bidx, B.bval, x, y, c, sm, lpr);
+            k_bsr_rows3<VT, 3, MODE><<<grid, 256, 0, st>>>(B.nbrows, B.nblocks, B.bptr, B.bidx, bval, x, y, c, sm, lpr);
         else
-            k_bsr_rows3<1, MODE><<<grid, 256, 0, st>>>(B.nbrows, B.nblocks, B.bptr, B.bidx, B.bval, x, y, c, sm, lpr);
+            k_bsr_rows3<VT, 1, MODE><<<grid, 256, 0, st>>>(B.nbrows, B.nblocks, B.bptr, B.bidx, bval, x, y, c, sm, lpr);
     } else {
-        k_bsr_rows1<MODE><<<bsr_grid(B.nbrows), 256, 0, st>>>(B.nbrows, B.nblocks, B.bptr, B.bidx, B.bval, x, y, c, sm);
+        k_bsr_rows1<VT, MODE><<<bsr_grid(B.nbrows), 256, 0, st>>>(B.nbrows, B.nblocks, B.bptr, B.bidx, bval, x, y, c, sm);
     }
     MWX_LAUNCH_CHECK();
     return 0;
 }
 
+template <int MODE>
+int bsr_launch(const DBsr &B, const double *x, double *y, const double *c, BsrSmoother sm, cudaStream_t st) {
+    if (B.bval32) return bsr_launch_t<float, MODE>(B, B.bval32, x, y, c, sm, st);       // fp32-stored planes
+    return bsr_launch_t<double, MODE>(B, B.bval, x, y, c, sm, st);
+}
+
+__global__ void k_f64_to_f32(int64_t n, const double *__restrict__ in, float *__restrict__ out) {
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st) out[i] = (float)in[i];
+}
+
 }  // namespace
 
 void free_bsr(DBsr &B) {
-    cudaFree(B.bptr); cudaFree(B.bidx); cudaFree(B.bval);
+    cudaFree(B.bptr); cudaFree(B.bidx); cudaFree(B.bval); cudaFree(B.bval32);
     B = DBsr();
+}
+
+// Keep the value planes in fp32 only (half the bytes of the operator); index arrays, x, y and the sums are unchanged.
+int bsr_store_fp32(DBsr &B, cudaStream_t st) {
+    if (!B.bptr || B.bval32 || !B.bval) return 0;
+    const int64_t n = B.nblocks * B.br * B.bc;
+    if (cudaMalloc((void **)&B.bval32, sizeof(float) * (size_t)(n ? n : 1)) != cudaSuccess) { B.bval32 = nullptr; return MWX_E_NOMEM; }
+    k_f64_to_f32<<<bsr_grid(n), 256, 0, st>>>(n, B.bval, B.bval32);
+    MWX_LAUNCH_CHECK();
+    MWX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(B.bval);
+    B.bval = nullptr;
+    return 0;
 }
 
 // Returns 0 and leaves out.bptr == nullptr when the operator does not have the block structure (the caller keeps the
@@ -234,8 +258,9 @@ int bsr_smoother_step(const DBsr &B, const double *x_in, double *x_out, const do
 
 // ---- C ABI: block-CSR twins for operators held outside an AMG hierarchy (the row blocks of the partitioned V-cycle) ----
 extern "C" int mwx_bsr_create(int64_t rows, int64_t cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
-                              const double *values, int32_t br, int32_t bc, void **out, void *stream) {
-    if (!out) return MWX_E_BADARG;
+                              const double *values, int32_t br, int32_t bc, int32_t storage_bits, void **out,
+                              void *stream) {
+    if (!out || (storage_bits != 64 && storage_bits != 32)) return MWX_E_BADARG;
     *out = nullptr;
     if (rows <= 0 || cols <= 0 || nnz <= 0 || !indptr || !indices || !values) return 0;
     mwx::DCsr A;
@@ -244,6 +269,10 @@ extern "C" int mwx_bsr_create(int64_t rows, int64_t cols, int64_t nnz, const int
     mwx::DBsr B;
     const int rc = mwx::bsr_from_csr(A, br, bc, B, mwx::as_stream(stream));
     if (rc) return rc;
+    if (B.bptr && storage_bits == 32) {
+        const int rc2 = mwx::bsr_store_fp32(B, mwx::as_stream(stream));
+        if (rc2) { mwx::free_bsr(B); return rc2; }
+    }
     if (B.bptr) *out = new mwx::DBsr(B);
     return 0;
 }

@@ -50,6 +50,10 @@ __device__ __forceinline__ bool fold_partials(double v_thread0, double *partials
 constexpr int SPMV_STAGE_ELEMS = SPMV_ROWS * 20 + 8;                 // staged nonzeros per stage (<= 20 per row)
 constexpr int SPMV_STAGE_BYTES = SPMV_STAGE_ELEMS * 12;             // 8 B value + 4 B column
 constexpr int SPMV_SMEM_BYTES = 2 * SPMV_STAGE_BYTES + 64 + 32 * 8; // + barriers/meta + reduction scratch
+// PK (fp32-stored operator, see PackedNz in krylov.cuh): one 8-byte (value, column) record per nonzero; the fp64
+// product overwrites the record it came from, so a stage is 8 B per nonzero and ONE bulk copy per tile.
+constexpr int SPMV_STAGE_BYTES_PK = SPMV_STAGE_ELEMS * 8;
+constexpr int SPMV_SMEM_BYTES_PK = 2 * SPMV_STAGE_BYTES_PK + 64 + 32 * 8;
 
 // MODE 0: y = A x   1: y = c - A x   2: y = c + A x      (c = `cvec`, may alias y for MODE 2)
 // MODE 3 (smoother step): d = c1 d + c2 dinv (c - A x);  y = x + d     (y must not alias x)
@@ -60,7 +64,7 @@ struct SmootherArgs { const double *dinv; double *d; double c1, c2; };
 // complete_tx), one tile ahead of the consumers; the 128 threads then only issue the x gathers (all of
 // a thread's gathers are in flight together), write the products back in place, and one thread per
 // row adds its products in CSR order.
-template <bool DOT, int MODE>
+template <bool DOT, int MODE, bool PK = false>
 __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
                                                     const int32_t *__restrict__ indices,
                                                     const double *__restrict__ values,
@@ -71,11 +75,13 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                                                     unsigned int *ticket, SmootherArgs sm, int tma_ok,
                                                     int rows_per_tile, int lanes_per_row) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    auto stage_vals = [&](int stage) { return reinterpret_cast<double *>(smem_raw + stage * SPMV_STAGE_BYTES); };
+    constexpr int STAGE_BYTES = PK ? SPMV_STAGE_BYTES_PK : SPMV_STAGE_BYTES;
+    const PackedNz *__restrict__ packed = reinterpret_cast<const PackedNz *>(values);     // PK: `values` is the packed array
+    auto stage_vals = [&](int stage) { return reinterpret_cast<double *>(smem_raw + stage * STAGE_BYTES); };
     auto stage_cols = [&](int stage) {
-        return reinterpret_cast<int32_t *>(smem_raw + stage * SPMV_STAGE_BYTES + SPMV_STAGE_ELEMS * 8);
+        return reinterpret_cast<int32_t *>(smem_raw + stage * STAGE_BYTES + SPMV_STAGE_ELEMS * 8);          // !PK only
     };
-    unsigned char *tail = smem_raw + 2 * SPMV_STAGE_BYTES;
+    unsigned char *tail = smem_raw + 2 * STAGE_BYTES;
     uint64_t *bar = reinterpret_cast<uint64_t *>(tail);                 // [2]
     int64_t *s_base = reinterpret_cast<int64_t *>(tail + 16);           // [2] first staged nonzero
     int32_t *s_nst = reinterpret_cast<int32_t *>(tail + 32);            // [2] staged count, -1 = direct path
@@ -104,9 +110,14 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
             s_base[stage] = base;
             s_nst[stage] = (int32_t)nst;
             fence_proxy_async();                                   // consumers' generic accesses -> before the refill
-            mbar_expect_tx(&bar[stage], (uint32_t)(nst * 12));
-            bulk_g2s(stage_vals(stage), values + base, (uint32_t)(nst * 8), &bar[stage]);
-            bulk_g2s(stage_cols(stage), indices + base, (uint32_t)(nst * 4), &bar[stage]);
+            if (PK) {
+                mbar_expect_tx(&bar[stage], (uint32_t)(nst * 8));
+                bulk_g2s(stage_vals(stage), packed + base, (uint32_t)(nst * 8), &bar[stage]);
+            } else {
+                mbar_expect_tx(&bar[stage], (uint32_t)(nst * 12));
+                bulk_g2s(stage_vals(stage), values + base, (uint32_t)(nst * 8), &bar[stage]);
+                bulk_g2s(stage_cols(stage), indices + base, (uint32_t)(nst * 4), &bar[stage]);
+            }
         } else {
             s_base[stage] = s0;
             s_nst[stage] = -1;
@@ -145,7 +156,13 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = tid * 2 + u * 2 * SPMV_THREADS;
-                c[u] = e < nst ? *reinterpret_cast<const int2 *>(cs + e) : make_int2(0, 0);
+                if (PK) {
+                    // two (value, column) records = 16 bytes; staged counts are multiples of 4, so the pair is in range
+                    const int4 rec = e < nst ? *reinterpret_cast<const int4 *>(vs + e) : make_int4(0, 0, 0, 0);
+                    c[u] = make_int2(rec.y, rec.w);             // the values are re-read from the stage below (registers)
+                } else {
+                    c[u] = e < nst ? *reinterpret_cast<const int2 *>(cs + e) : make_int2(0, 0);
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -156,7 +173,13 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
             for (int u = 0; u < U; ++u) {
                 const int e = tid * 2 + u * 2 * SPMV_THREADS;
                 if (e < nst) {
-                    double2 v = *reinterpret_cast<double2 *>(vs + e);
+                    double2 v;
+                    if (PK) {
+                        const float4 rec = *reinterpret_cast<const float4 *>(vs + e);
+                        v = make_double2((double)rec.x, (double)rec.z);
+                    } else {
+                        v = *reinterpret_cast<double2 *>(vs + e);
+                    }
                     v.x *= xa[u];
                     v.y *= xb[u];
                     *reinterpret_cast<double2 *>(vs + e) = v;
@@ -182,6 +205,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                 double sum = 0.0;
                 if (nst >= 0) {
                     for (int e = (int)(a - base); e < (int)(b - base); ++e) sum += vs[e];
+                } else if (PK) {
+                    for (int64_t e = a; e < b; ++e) { const PackedNz q = packed[e]; sum += (double)q.v * __ldg(x + q.c); }
                 } else {
                     for (int64_t e = a; e < b; ++e) sum += values[e] * __ldg(x + indices[e]);
                 }
@@ -199,6 +224,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                     const int64_t a = indptr[r], b = indptr[r + 1];
                     if (nst >= 0) {
                         for (int e = (int)(a - base) + sub; e < (int)(b - base); e += lpr) sum += vs[e];
+                    } else if (PK) {
+                        for (int64_t e = a + sub; e < b; e += lpr) { const PackedNz q = packed[e]; sum += (double)q.v * __ldg(x + q.c); }
                     } else {
                         for (int64_t e = a + sub; e < b; e += lpr) sum += values[e] * __ldg(x + indices[e]);
                     }
@@ -399,27 +426,40 @@ int spmv_plan_rows(int64_t n, const int64_t *indptr, int *rows_out, cudaStream_t
 
 namespace {
 
-template <bool DOT, int MODE>
+// PK: `values` points at the packed (fp32 value, column) records and `indices` is unused.
+template <bool DOT, int MODE, bool PK = false>
 int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
                 double *y, const double *c, const double *dot_with, double *dot_out, double *partials,
                 unsigned int *ticket, SmootherArgs sm, cudaStream_t st) {
     static int ctas_per_sm = 0;                   // per instantiation; the attributes are per device function
+    constexpr int SMEM = PK ? SPMV_SMEM_BYTES_PK : SPMV_SMEM_BYTES;
     if (!ctas_per_sm) {
-        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_BYTES));
-        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int occ = 0;
-        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<DOT, MODE>, SPMV_THREADS, SPMV_SMEM_BYTES));
+        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<DOT, MODE, PK>, SPMV_THREADS, SMEM));
         ctas_per_sm = occ > 0 ? occ : 1;
     }
     // TMA bulk copies need 16-byte aligned global addresses; the kernel aligns offsets, the bases must be too
-    const int tma_ok = (((uintptr_t)values & 15) == 0 && ((uintptr_t)indices & 15) == 0) ? 1 : 0;
+    const int tma_ok = (((uintptr_t)values & 15) == 0 && (PK || ((uintptr_t)indices & 15) == 0)) ? 1 : 0;
     // nnz <= -8: a plan from spmv_plan_rows = -(tile height + 4096 * log2(lanes per row))
     const int plan = nnz <= -8 ? (int)(-nnz) : spmv_rows_per_tile(n, nnz);
     const int rows = plan & 4095, lanes = 1 << (plan >> 12);
-    k_spmv<DOT, MODE><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SPMV_SMEM_BYTES, st>>>(
+    k_spmv<DOT, MODE, PK><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SMEM, st>>>(
         n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows, lanes);
     MWX_LAUNCH_CHECK();
     return 0;
+}
+
+__global__ void k_csr_pack(int64_t nnz, const int32_t *__restrict__ indices, const double *__restrict__ values,
+                           PackedNz *__restrict__ out) {
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += st) {
+        PackedNz q;
+        q.v = (float)values[k];
+        q.c = indices[k];
+        out[k] = q;
+    }
 }
 
 }  // namespace
@@ -448,6 +488,36 @@ int launch_smoother_step(int64_t n, int64_t nnz, const int64_t *indptr, const in
                          double c1, double c2, cudaStream_t st) {
     return spmv_launch<false, 3>(n, nnz, indptr, indices, values, x_in, x_out, b, nullptr, nullptr, nullptr, nullptr,
                                  SmootherArgs{dinv, d, c1, c2}, st);
+}
+
+// fp32-stored twins: the same kernels reading 8-byte (fp32 value, column) records; vectors and sums stay fp64.
+int csr_pack(int64_t nnz, const int32_t *indices, const double *values, PackedNz *out, cudaStream_t st) {
+    if (nnz <= 0) return 0;
+    k_csr_pack<<<vec_grid(nnz), VEC_THREADS, 0, st>>>(nnz, indices, values, out);
+    MWX_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_spmv_pk(int64_t n, int64_t nnz, const int64_t *indptr, const PackedNz *pk, const double *x, double *y,
+                   cudaStream_t st) {
+    return spmv_launch<false, 0, true>(n, nnz, indptr, nullptr, reinterpret_cast<const double *>(pk), x, y, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, SmootherArgs{}, st);
+}
+
+int launch_spmv_axpy_pk(int64_t n, int64_t nnz, const int64_t *indptr, const PackedNz *pk, const double *x, double *y,
+                        const double *c, int sign, cudaStream_t st) {
+    if (sign < 0)
+        return spmv_launch<false, 1, true>(n, nnz, indptr, nullptr, reinterpret_cast<const double *>(pk), x, y, c, nullptr,
+                                           nullptr, nullptr, nullptr, SmootherArgs{}, st);
+    return spmv_launch<false, 2, true>(n, nnz, indptr, nullptr, reinterpret_cast<const double *>(pk), x, y, c, nullptr,
+                                       nullptr, nullptr, nullptr, SmootherArgs{}, st);
+}
+
+int launch_smoother_step_pk(int64_t n, int64_t nnz, const int64_t *indptr, const PackedNz *pk, const double *x_in,
+                            double *x_out, const double *b, const double *dinv, double *d, double c1, double c2,
+                            cudaStream_t st) {
+    return spmv_launch<false, 3, true>(n, nnz, indptr, nullptr, reinterpret_cast<const double *>(pk), x_in, x_out, b, nullptr,
+                                       nullptr, nullptr, nullptr, SmootherArgs{dinv, d, c1, c2}, st);
 }
 
 int launch_residual(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
@@ -700,4 +770,30 @@ extern "C" int mwx_dcg_residual(int64_t n, const int64_t *indptr, const int32_t 
                                 void *stream) {
     if (n <= 0 || !indptr || !indices || !values || !x_ext || !b || !r || !ws) return MWX_E_BADARG;
     return launch_residual(n, indptr, indices, values, x_ext, b, r, dinv, ws_scalars(ws), ws_partials(ws), as_stream(stream));
+}
+
+// fp32-stored twin of a CSR operator for the kernels above (row blocks of the partitioned V-cycle): packed must hold
+// nnz 8-byte records, 16-byte aligned.
+extern "C" int mwx_csr_pack(int64_t nnz, const int32_t *indices, const double *values, void *packed, void *stream) {
+    if (nnz < 0 || (nnz && (!indices || !values || !packed))) return MWX_E_BADARG;
+    return csr_pack(nnz, indices, values, (PackedNz *)packed, as_stream(stream));
+}
+
+extern "C" int mwx_spmv_pk(int64_t n, int64_t nnz, const int64_t *indptr, const void *packed, const double *x, double *y,
+                           void *stream) {
+    if (n <= 0 || !indptr || !packed || !x || !y) return MWX_E_BADARG;
+    return launch_spmv_pk(n, nnz, indptr, (const PackedNz *)packed, x, y, as_stream(stream));
+}
+
+extern "C" int mwx_spmv_axpy_pk(int64_t n, int64_t nnz, const int64_t *indptr, const void *packed, const double *x,
+                                const double *c, int32_t sign, double *y, void *stream) {
+    if (n <= 0 || !indptr || !packed || !x || !c || !y || sign == 0) return MWX_E_BADARG;
+    return launch_spmv_axpy_pk(n, nnz, indptr, (const PackedNz *)packed, x, y, c, sign, as_stream(stream));
+}
+
+extern "C" int mwx_smoother_step_pk(int64_t n, int64_t nnz, const int64_t *indptr, const void *packed, const double *x_in,
+                                    double *x_out, const double *b, const double *dinv, double *d, double c1, double c2,
+                                    void *stream) {
+    if (n <= 0 || !indptr || !packed || !x_in || !x_out || !b || !dinv || !d || x_in == x_out) return MWX_E_BADARG;
+    return launch_smoother_step_pk(n, nnz, indptr, (const PackedNz *)packed, x_in, x_out, b, dinv, d, c1, c2, as_stream(stream));
 }

@@ -40,6 +40,19 @@ int launch_residual(int64_t n, const int64_t *indptr, const int32_t *indices, co
                     const double *x, const double *b, double *r, const double *dinv, CgScalars *sc,
                     double *partials, cudaStream_t st);
 
+// fp32-STORED operator (the AMG hierarchy of mode 'sa'): one 8-byte record per nonzero instead of 8 + 4 bytes in two
+// arrays.  Only the storage is single precision - x, y, the products and the row sums are fp64 - so the operator applied
+// is exactly the linear operator of the rounded matrix (symmetric where the fp64 one is).
+struct PackedNz { float v; int32_t c; };
+int csr_pack(int64_t nnz, const int32_t *indices, const double *values, PackedNz *out, cudaStream_t st);
+int launch_spmv_pk(int64_t n, int64_t nnz, const int64_t *indptr, const PackedNz *pk, const double *x, double *y,
+                   cudaStream_t st);
+int launch_spmv_axpy_pk(int64_t n, int64_t nnz, const int64_t *indptr, const PackedNz *pk, const double *x, double *y,
+                        const double *c, int sign, cudaStream_t st);
+int launch_smoother_step_pk(int64_t n, int64_t nnz, const int64_t *indptr, const PackedNz *pk, const double *x_in,
+                            double *x_out, const double *b, const double *dinv, double *d, double c1, double c2,
+                            cudaStream_t st);
+
 // diag[i] = A[i,i] (invert != 0: its reciprocal).
 int launch_csr_diagonal(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
                         double *diag, int invert, cudaStream_t st);

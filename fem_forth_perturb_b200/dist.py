@@ -97,17 +97,25 @@ class HaloPlan:
             self.send[peer] = (ids - self.clo).to(L.require_cuda().int32).contiguous()
 
 
+def pack_fp32(cols, vals):
+    """fp32-stored twin of a CSR operator: one 8-byte (fp32 value, int32 column) record per nonzero (krylov.cu)."""
+    torch = L.require_cuda()
+    out = torch.empty(max(int(vals.numel()), 2), dtype=torch.int64, device=vals.device)        # 8 B per record, 16-B aligned
+    L.check(L.lib().mwx_csr_pack(vals.numel(), L.ptr(cols), L.ptr(vals), L.ptr(out), L.stream()), 'mwx_csr_pack')
+    return out
+
+
 class LocalOp(HaloPlan):
     """Rows [rlo, rhi) of a global CSR operator (device tensors), columns renumbered to [owned | ghost]."""
 
-    def __init__(self, indptr, indices, values, rlo, rhi, col_offsets, rank, block=None):
+    def __init__(self, indptr, indices, values, rlo, rhi, col_offsets, rank, block=None, fp32=False):
         """block = (br, bc): also build the block-CSR twin (csrc/bsr.cu) when the local operator has that structure -
         owned columns start at a block boundary and ghosts come in whole blocks for the operators of a
         smoothed-aggregation hierarchy; the kernels behind CudaOps then use it (``self.bsr``)."""
         torch = L.require_cuda()
         dev = values.device
         self.rank, self.nloc = rank, rhi - rlo
-        self.bsr = None
+        self.bsr, self.pk = None, None
         self.clo, self.ncol = col_offsets[rank], col_offsets[rank + 1] - col_offsets[rank]
         s0, s1 = int(indptr[rlo].item()), int(indptr[rhi].item())
         self.indptr = (indptr[rlo:rhi + 1] - s0).contiguous()
@@ -128,9 +136,11 @@ class LocalOp(HaloPlan):
         if block is not None and self.nnz > 0 and os.environ.get('MWX_BSR', '1') != '0':
             h = ctypes.c_void_p()
             L.check(L.lib().mwx_bsr_create(self.nloc, self.ncol + self.nghost, self.nnz, L.ptr(self.indptr), L.ptr(self.cols),
-                                           L.ptr(self.vals), int(block[0]), int(block[1]), ctypes.byref(h), L.stream()),
-                    'mwx_bsr_create')
+                                           L.ptr(self.vals), int(block[0]), int(block[1]), 32 if fp32 else 64, ctypes.byref(h),
+                                           L.stream()), 'mwx_bsr_create')
             self.bsr = h if h.value else None
+        if fp32 and self.bsr is None and self.nnz > 0 and os.environ.get('MWX_PACKED_CSR', '0') != '0':
+            self.pk = pack_fp32(self.cols, self.vals)      # scalar operators: measured slower than fp64 CSR (amg.cu), A/B only
 
     def __del__(self):
         try:
@@ -703,6 +713,9 @@ class CudaOps:
     def spmv(self, p, x_ext, y):
         if getattr(p, 'bsr', None):
             return self._emit('mwx_bsr_spmv', L.lib().mwx_bsr_spmv, p.bsr, L.ptr(x_ext), L.ptr(y), L.stream())
+        if getattr(p, 'pk', None) is not None:
+            return self._emit('mwx_spmv_pk', L.lib().mwx_spmv_pk, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.pk),
+                              L.ptr(x_ext), L.ptr(y), L.stream())
         self._emit('mwx_spmv', L.lib().mwx_spmv, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals),
                    L.ptr(x_ext), L.ptr(y), L.stream())
 
@@ -710,6 +723,9 @@ class CudaOps:
         if getattr(p, 'bsr', None):
             return self._emit('mwx_bsr_spmv_axpy', L.lib().mwx_bsr_spmv_axpy, p.bsr, L.ptr(x_ext), L.ptr(c), int(sign),
                               L.ptr(y), L.stream())
+        if getattr(p, 'pk', None) is not None:
+            return self._emit('mwx_spmv_axpy_pk', L.lib().mwx_spmv_axpy_pk, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.pk),
+                              L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
         self._emit('mwx_spmv_axpy', L.lib().mwx_spmv_axpy, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
 
@@ -721,6 +737,10 @@ class CudaOps:
         if getattr(p, 'bsr', None):
             return self._emit('mwx_bsr_smoother_step', L.lib().mwx_bsr_smoother_step, p.bsr, L.ptr(x_in), L.ptr(x_out),
                               L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2), L.stream())
+        if getattr(p, 'pk', None) is not None:
+            return self._emit('mwx_smoother_step_pk', L.lib().mwx_smoother_step_pk, p.nloc, p.spmv_hint, L.ptr(p.indptr),
+                              L.ptr(p.pk), L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2),
+                              L.stream())
         self._emit('mwx_smoother_step', L.lib().mwx_smoother_step, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2),
                    L.stream())
@@ -981,6 +1001,8 @@ class DistAMG:
         self.parts, self.comm, self.ops = parts, comm, ops or CudaOps()
         self.degree, self.ratio = int(degree), float(ratio)
         self._programs, self._tail_out = {}, None
+        # mode 'sa': operators of the hierarchy stored in fp32 as on one GPU (AMGHierarchy._default_storage)
+        self.storage_bits = 32 if (mode == 'sa' and os.environ.get('MWX_SA_FP32', '1') != '0') else 64
         dev = parts[0].vals.device
         world = comm.world
         offsets0 = parts[0].partition.offsets
@@ -1038,9 +1060,19 @@ class DistAMG:
                 wide = 3 if mode == 'sa' else None
                 blk = (lambda br, bc: (br, bc)) if wide else (lambda br, bc: None)
                 fine = 1 if l == 0 else wide
-                lv['A'].append(p if l == 0 else LocalOp(*A_full, offs[l][r], offs[l][r + 1], offs[l], r, block=blk(wide, wide)))
-                lv['P'].append(LocalOp(*P_full, offs[l][r], offs[l][r + 1], offs[l + 1], r, block=blk(fine, wide)))
-                lv['R'].append(LocalOp(*R_full, offs[l + 1][r], offs[l + 1][r + 1], offs[l], r, block=blk(wide, fine)))
+                f32 = self.storage_bits == 32
+                if l == 0 and f32 and os.environ.get('MWX_PACKED_CSR', '0') != '0':
+                    # (A/B switch) the V-cycle smooths with the fp32-stored twin of the rank's fine rows; CG keeps multiplying
+                    # with the fp64 values of `p` itself (a shallow copy: same halo plan, own kernel arguments)
+                    import copy
+                    a0 = copy.copy(p)
+                    a0.pk = pack_fp32(p.cols, p.vals)
+                    lv['A'].append(a0)
+                else:
+                    lv['A'].append(p if l == 0 else LocalOp(*A_full, offs[l][r], offs[l][r + 1], offs[l], r,
+                                                            block=blk(wide, wide), fp32=f32))
+                lv['P'].append(LocalOp(*P_full, offs[l][r], offs[l][r + 1], offs[l + 1], r, block=blk(fine, wide), fp32=f32))
+                lv['R'].append(LocalOp(*R_full, offs[l + 1][r], offs[l + 1][r + 1], offs[l], r, block=blk(wide, fine), fp32=f32))
             for key in ('A', 'P', 'R'):
                 if not (key == 'A' and l == 0):
                     comm.exchange_requests(lv[key])

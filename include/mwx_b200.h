@@ -398,11 +398,32 @@ int mwx_gather_f64_i64(int64_t n, const double *src, const int64_t *idx, double 
 int mwx_halo_push(int64_t total, int32_t nseg, const int64_t *seg, const int32_t *idx, const double *v,
                   double *const *dst, void *stream);
 
+/* fp32-STORED hierarchy (mode 'sa', throughput; no reference counterpart).  The operators a V-cycle applies are read
+ * once per application and dominate its HBM traffic; storing their VALUES in single precision - vectors, products and
+ * row sums stay fp64 - halves those bytes for the block-CSR operators (8.4 -> 4.4 B per nonzero).  Scalar CSR operators
+ * (the fine matrix) keep fp64: their kernel is bound by the x gathers, and the packed (fp32 value, int32 column) record
+ * layout below (12 -> 8 B per nonzero) measured slower - it is built only under MWX_PACKED_CSR=1.  The preconditioner
+ * is exactly the V-cycle of the rounded hierarchy: a fixed symmetric linear operator, so CG's theory holds; iteration
+ * counts are unchanged at 67 M DOFs.  The system matrix CG multiplies with is never touched.  bits: 32 or 64 (no-op);
+ * parity mode ignores the call. */
+int mwx_amg_set_storage(mwx_amg_dev_t *d, int32_t bits, void *stream);
+/* The same for operators held outside a hierarchy (row blocks of the partitioned V-cycle): packed = nnz 8-byte records
+ * (16-byte aligned); the _pk kernels are mwx_spmv / mwx_spmv_axpy / mwx_smoother_step reading those records. */
+int mwx_csr_pack(int64_t nnz, const int32_t *indices, const double *values, void *packed, void *stream);
+int mwx_spmv_pk(int64_t n, int64_t nnz_hint, const int64_t *indptr, const void *packed, const double *x, double *y,
+                void *stream);
+int mwx_spmv_axpy_pk(int64_t n, int64_t nnz_hint, const int64_t *indptr, const void *packed, const double *x,
+                     const double *c, int32_t sign, double *y, void *stream);
+int mwx_smoother_step_pk(int64_t n, int64_t nnz_hint, const int64_t *indptr, const void *packed, const double *x_in,
+                         double *x_out, const double *b, const double *dinv, double *d, double c1, double c2,
+                         void *stream);
+
 /* Block-CSR twin of a CSR operator whose nonzeros come in br x bc blocks (3x3, 1x3, 3x1: the coarse operators of a
  * smoothed-aggregation hierarchy on three candidates); *out = NULL (status 0) when the operator is not blocked that way.
- * Used for the row blocks of the partitioned V-cycle; inside a single-GPU hierarchy the library builds them itself. */
+ * Used for the row blocks of the partitioned V-cycle; inside a single-GPU hierarchy the library builds them itself.
+ * storage_bits = 32 keeps the value planes in fp32 (see mwx_amg_set_storage), 64 in fp64. */
 int mwx_bsr_create(int64_t rows, int64_t cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
-                   const double *values, int32_t br, int32_t bc, void **out, void *stream);
+                   const double *values, int32_t br, int32_t bc, int32_t storage_bits, void **out, void *stream);
 void mwx_bsr_destroy(void *bsr);
 int mwx_bsr_spmv(const void *bsr, const double *x, double *y, void *stream);                       /* y = A x */
 int mwx_bsr_spmv_axpy(const void *bsr, const double *x, const double *c, int32_t sign, double *y,

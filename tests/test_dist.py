@@ -214,7 +214,9 @@ def test_distributed_smoothed_aggregation_matches_single_gpu(cuda, monkeypatch, 
     single = F.AMGHierarchy(Kp, mode='sa', reorder=False)
     z_ref = single.precondition(b_new)
     z = torch.cat(amg.apply([b_new[p.lo:p.hi].clone() for p in prob.parts]))
-    assert float(torch.linalg.norm(z - z_ref) / torch.linalg.norm(z_ref)) < 1e-8
+    # both hierarchies are STORED in fp32: the ranks round the rows they assembled themselves, which agree with the
+    # globally assembled matrix to 1e-13 only - an entry on a rounding boundary differs by one fp32 ulp
+    assert float(torch.linalg.norm(z - z_ref) / torch.linalg.norm(z_ref)) < 2e-6
     xs, its, info, _ = D.dist_pcg(prob.parts, prob.comm, [b_new[p.lo:p.hi].clone() for p in prob.parts], tol=1e-8,
                                   precond='amg', amg=amg)
     x1, its1, info1, _ = _run_pcg(Kp, b_new, 1e-8, None, amg=single, reordering=None)

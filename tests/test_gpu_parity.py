@@ -603,15 +603,19 @@ def test_block_csr_kernels_match_the_scalar_spmv(cuda, monkeypatch):
     Kc = F.condense(K, D=D, expand=False)
     r = torch.from_numpy(np.random.default_rng(8).standard_normal(Kc.shape[0])).cuda()
     monkeypatch.setenv('MWX_SA_MAX_COARSE', '300')
-    monkeypatch.setenv('MWX_BSR', '1')
-    ml_b = F.AMGHierarchy(Kc, mode='sa')
-    monkeypatch.setenv('MWX_BSR', '0')
-    ml_s = F.AMGHierarchy(Kc, mode='sa')
-    assert ml_b.levels >= 4 and ml_b.level_sizes() == ml_s.level_sizes()
-    for gamma, k in ((1, 0), (2, 9)):
-        ml_b.set_cycle(gamma, k); ml_s.set_cycle(gamma, k)
-        zb, zs = ml_b.precondition(r), ml_s.precondition(r)
-        assert float(torch.linalg.norm(zb - zs) / torch.linalg.norm(zs)) < 1e-12
+    monkeypatch.setenv('MWX_PACKED_CSR', '1')      # fp32 storage: the scalar kernels read the same rounded values (packed records)
+    for fp32 in ('0', '1'):                        # fp64-stored, then fp32-stored operators
+        monkeypatch.setenv('MWX_SA_FP32', fp32)
+        monkeypatch.setenv('MWX_BSR', '1')
+        ml_b = F.AMGHierarchy(Kc, mode='sa')
+        monkeypatch.setenv('MWX_BSR', '0')
+        ml_s = F.AMGHierarchy(Kc, mode='sa')
+        assert ml_b.levels >= 4 and ml_b.level_sizes() == ml_s.level_sizes()
+        assert ml_b.storage_bits == ml_s.storage_bits == (32 if fp32 == '1' else 64)
+        for gamma, k in ((1, 0), (2, 9)):
+            ml_b.set_cycle(gamma, k); ml_s.set_cycle(gamma, k)
+            zb, zs = ml_b.precondition(r), ml_s.precondition(r)
+            assert float(torch.linalg.norm(zb - zs) / torch.linalg.norm(zs)) < 1e-12
     # the gamma = 2 cycle is still a symmetric operator (CG needs that)
     s2 = torch.from_numpy(np.random.default_rng(9).standard_normal(Kc.shape[0])).cuda()
     a, b = float(torch.dot(s2, ml_b.precondition(r))), float(torch.dot(r, ml_b.precondition(s2)))
@@ -622,6 +626,67 @@ def test_block_csr_kernels_match_the_scalar_spmv(cuda, monkeypatch):
     x1, it1, info1, _ = F.pcg(Kc, b_rhs, tol=1e-10, amg=ml_b)
     assert info1 == 0 and info2 == 0 and it2 < it1
     assert float(torch.linalg.norm(x1 - x2) / torch.linalg.norm(x1)) < 1e-7
+
+
+def test_fp32_stored_hierarchy(cuda, monkeypatch):
+    """mode='sa' stores the operators of its hierarchy in fp32 (values only; vectors and sums fp64).  The packed-record
+    SpMV equals the fp64 SpMV of the ROUNDED matrix to round-off; the V-cycle stays a symmetric operator, differs from the
+    fp64-stored one at the 1e-7 level only, and CG converges to the same solution in (nearly) the same iterations."""
+    import ctypes
+    import fem_forth_perturb_b200 as F
+    from fem_forth_perturb_b200 import _lib as L
+    torch = cuda
+    gm = F.MeshTri().refine(7)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    K = F.asm_gpu(1e-4 * F.a_load + F.b_load, basis)
+    bf = gm.boundary_facets()
+    D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+    Kc = F.condense(K, D=D, expand=False)
+    n = Kc.shape[0]
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.standard_normal(n)).cuda()
+    # ---- kernels: y = A32 x, c -+ A32 x, smoother step on packed (fp32 value, column) records
+    pk = torch.empty(Kc.nnz, dtype=torch.int64, device='cuda')
+    L.check(L.lib().mwx_csr_pack(Kc.nnz, L.ptr(Kc.d_indices), L.ptr(Kc.d_data), L.ptr(pk), L.stream()), 'mwx_csr_pack')
+    A32 = sp.csr_matrix((Kc.d_data.cpu().numpy().astype(np.float32).astype(np.float64), Kc.d_indices.cpu().numpy(),
+                         Kc.d_indptr.cpu().numpy()), shape=Kc.shape)
+    y = torch.empty(n, dtype=torch.float64, device='cuda')
+    L.check(L.lib().mwx_spmv_pk(n, Kc.spmv_hint(), L.ptr(Kc.d_indptr), L.ptr(pk), L.ptr(x), L.ptr(y), L.stream()), 'mwx_spmv_pk')
+    ref = A32 @ x.cpu().numpy()
+    assert np.abs(y.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(ref - Kc.tocsr() @ x.cpu().numpy()).max() > 1e-9 * np.abs(ref).max()        # it IS the rounded operator
+    c = torch.from_numpy(rng.standard_normal(n)).cuda()
+    for sign in (-1, 1):
+        L.check(L.lib().mwx_spmv_axpy_pk(n, Kc.spmv_hint(), L.ptr(Kc.d_indptr), L.ptr(pk), L.ptr(x), L.ptr(c), sign, L.ptr(y),
+                                         L.stream()), 'mwx_spmv_axpy_pk')
+        assert np.abs(y.cpu().numpy() - (c.cpu().numpy() + sign * ref)).max() <= 1e-13 * np.abs(ref).max()
+    dinv = torch.from_numpy(1.0 / Kc.tocsr().diagonal()).cuda()
+    d = torch.from_numpy(rng.standard_normal(n)).cuda()
+    d0 = d.cpu().numpy().copy()
+    L.check(L.lib().mwx_smoother_step_pk(n, Kc.spmv_hint(), L.ptr(Kc.d_indptr), L.ptr(pk), L.ptr(x), L.ptr(y), L.ptr(c),
+                                         L.ptr(dinv), L.ptr(d), 0.3, 0.7, L.stream()), 'mwx_smoother_step_pk')
+    dn = 0.3 * d0 + 0.7 * dinv.cpu().numpy() * (c.cpu().numpy() - ref)
+    assert np.abs(d.cpu().numpy() - dn).max() <= 1e-12 * np.abs(dn).max()
+    assert np.abs(y.cpu().numpy() - (x.cpu().numpy() + dn)).max() <= 1e-12 * np.abs(dn).max()
+    # ---- hierarchy: fp32-stored (default: block-CSR planes; here the packed twins of the scalar operators too) against fp64
+    monkeypatch.setenv('MWX_PACKED_CSR', '1')
+    ml32 = F.AMGHierarchy(Kc, mode='sa')
+    monkeypatch.setenv('MWX_SA_FP32', '0')
+    ml64 = F.AMGHierarchy(Kc, mode='sa')
+    assert ml32.storage_bits == 32 and ml64.storage_bits == 64 and ml32.level_sizes() == ml64.level_sizes()
+    r = torch.from_numpy(rng.standard_normal(n)).cuda()
+    s2 = torch.from_numpy(rng.standard_normal(n)).cuda()
+    z32, z64 = ml32.precondition(r), ml64.precondition(r)
+    rel = float(torch.linalg.norm(z32 - z64) / torch.linalg.norm(z64))
+    assert 0.0 < rel < 1e-5, rel
+    a, b = float(torch.dot(s2, ml32.precondition(r))), float(torch.dot(r, ml32.precondition(s2)))
+    assert abs(a - b) <= 1e-10 * abs(a)                                   # still symmetric: a valid CG preconditioner
+    b_rhs = Kc.dot(x)
+    x32, it32, info32, _ = F.pcg(Kc, b_rhs, tol=1e-10, amg=ml32)
+    x64, it64, info64, _ = F.pcg(Kc, b_rhs, tol=1e-10, amg=ml64)
+    assert info32 == 0 and info64 == 0 and abs(it32 - it64) <= 2, (it32, it64)
+    assert float(torch.linalg.norm(x32 - x64) / torch.linalg.norm(x64)) < 1e-7
+    assert float(torch.linalg.norm(x32 - x) / torch.linalg.norm(x)) < 1e-6
 
 
 def test_locality_reordering_is_a_similarity_transform(cuda):
