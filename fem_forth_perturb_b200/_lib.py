@@ -54,6 +54,12 @@ _SIGNATURES = {
     'mwx_halo_push': [i64, i32, vp, vp, vp, vp, vp],
     'mwx_bsr_create': [i64, i64, i64, vp, vp, vp, i32, i32, i32, ctypes.POINTER(vp), vp],
     'mwx_amg_set_storage': [vp, i32, vp],
+    'mwx_spmv_lx_create': [i64, vp, vp, i64, ctypes.POINTER(vp), vp],
+    'mwx_spmv_lx_destroy': [vp],
+    'mwx_spmv_lx': [i64, i64, vp, vp, vp, vp, vp, vp, vp],
+    'mwx_spmv_axpy_lx': [i64, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp],
+    'mwx_smoother_step_lx': [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, f64, vp],
+    'mwx_dcg_spmv_dot_lx': [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     'mwx_csr_pack': [i64, vp, vp, vp, vp],
     'mwx_spmv_pk': [i64, i64, vp, vp, vp, vp, vp],
     'mwx_spmv_axpy_pk': [i64, i64, vp, vp, vp, vp, i32, vp, vp],
@@ -115,7 +121,7 @@ _SIGNATURES = {
     'mwx_pcg_jacobi_history': [i64, vp, vp, vp, vp, vp, f64, i64, i32, vp, _pi64, _pi32, _pf64, vp, i64, vp],
     'mwx_pcg_amg': [vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, _pi64, _pi32, _pf64, vp],
 }
-_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev', 'mwx_asm_plan_destroy', 'mwx_bsr_destroy'}
+_VOID = {'mwx_amg_destroy_host', 'mwx_amg_destroy_dev', 'mwx_asm_plan_destroy', 'mwx_bsr_destroy', 'mwx_spmv_lx_destroy'}
 
 ERRORS = {-1: 'MWX_E_BADARG', -2: 'MWX_E_CAPACITY', -3: 'MWX_E_NOCONV', -4: 'MWX_E_NOMEM'}
 

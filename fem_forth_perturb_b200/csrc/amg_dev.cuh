@@ -26,6 +26,7 @@ struct DCsr {
     double *val = nullptr;
     DBsr bsr;                                  // set (bptr != nullptr) when the V-cycle should use the block kernels
     PackedNz *pk = nullptr;                    // fp32-stored twin of a scalar operator (krylov.cuh), used instead of idx/val
+    SpmvLX *lx = nullptr;                      // tile-local column plan of a scalar operator (spmv_lx.cu)
 };
 
 // One direction of the exact lexicographic Gauss-Seidel sweep, level-scheduled: rows grouped by dependency wavefront,

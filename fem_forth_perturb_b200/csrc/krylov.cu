@@ -54,6 +54,15 @@ constexpr int SPMV_SMEM_BYTES = 2 * SPMV_STAGE_BYTES + 64 + 32 * 8; // + barrier
 // product overwrites the record it came from, so a stage is 8 B per nonzero and ONE bulk copy per tile.
 constexpr int SPMV_STAGE_BYTES_PK = SPMV_STAGE_ELEMS * 8;
 constexpr int SPMV_SMEM_BYTES_PK = 2 * SPMV_STAGE_BYTES_PK + 64 + 32 * 8;
+// LX (tile-local columns, spmv_lx.cu): a stage = values (8 B) + 2-byte local indices + the tile's distinct columns;
+// one buffer of gathered x entries per CTA.
+constexpr int SPMV_LX_LIDX_OFF = SPMV_STAGE_ELEMS * 8;
+constexpr int SPMV_LX_UCOL_OFF = SPMV_LX_LIDX_OFF + SPMV_STAGE_ELEMS * 2;
+constexpr int SPMV_STAGE_BYTES_LX = SPMV_LX_UCOL_OFF + LX_MAX_U * 4;
+constexpr int SPMV_SMEM_BYTES_LX = 2 * SPMV_STAGE_BYTES_LX + 2 * LX_MAX_U * 8 + 64 + 32 * 8;
+static_assert(SPMV_LX_LIDX_OFF % 16 == 0 && SPMV_LX_UCOL_OFF % 16 == 0 && SPMV_STAGE_BYTES_LX % 16 == 0, "TMA alignment");
+enum { FMT_CSR = 0, FMT_PK = 1, FMT_LX = 2 };
+struct LxArgs { const int32_t *uptr; const int32_t *ucols; const uint16_t *lidx; };
 
 // MODE 0: y = A x   1: y = c - A x   2: y = c + A x      (c = `cvec`, may alias y for MODE 2)
 // MODE 3 (smoother step): d = c1 d + c2 dinv (c - A x);  y = x + d     (y must not alias x)
@@ -64,7 +73,7 @@ struct SmootherArgs { const double *dinv; double *d; double c1, c2; };
 // complete_tx), one tile ahead of the consumers; the 128 threads then only issue the x gathers (all of
 // a thread's gathers are in flight together), write the products back in place, and one thread per
 // row adds its products in CSR order.
-template <bool DOT, int MODE, bool PK = false>
+template <bool DOT, int MODE, int FMT = FMT_CSR>
 __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
                                                     const int32_t *__restrict__ indices,
                                                     const double *__restrict__ values,
@@ -73,18 +82,24 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                                                     const double *__restrict__ dot_with,
                                                     double *__restrict__ dot_out, double *partials,
                                                     unsigned int *ticket, SmootherArgs sm, int tma_ok,
-                                                    int rows_per_tile, int lanes_per_row) {
+                                                    int rows_per_tile, int lanes_per_row, LxArgs lx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int STAGE_BYTES = PK ? SPMV_STAGE_BYTES_PK : SPMV_STAGE_BYTES;
+    constexpr bool PK = FMT == FMT_PK, LX = FMT == FMT_LX;
+    constexpr int STAGE_BYTES = PK ? SPMV_STAGE_BYTES_PK : (LX ? SPMV_STAGE_BYTES_LX : SPMV_STAGE_BYTES);
     const PackedNz *__restrict__ packed = reinterpret_cast<const PackedNz *>(values);     // PK: `values` is the packed array
     auto stage_vals = [&](int stage) { return reinterpret_cast<double *>(smem_raw + stage * STAGE_BYTES); };
     auto stage_cols = [&](int stage) {
         return reinterpret_cast<int32_t *>(smem_raw + stage * STAGE_BYTES + SPMV_STAGE_ELEMS * 8);          // !PK only
     };
-    unsigned char *tail = smem_raw + 2 * STAGE_BYTES;
+    auto stage_lidx = [&](int stage) { return reinterpret_cast<uint16_t *>(smem_raw + stage * STAGE_BYTES + SPMV_LX_LIDX_OFF); };
+    auto stage_ucol = [&](int stage) { return reinterpret_cast<int32_t *>(smem_raw + stage * STAGE_BYTES + SPMV_LX_UCOL_OFF); };
+    // LX: gathered x entries of the staged tile, one buffer per stage (the next tile's are fetched during this tile's row sums)
+    auto stage_xs = [&](int stage) { return reinterpret_cast<double *>(smem_raw + 2 * STAGE_BYTES + stage * LX_MAX_U * 8); };
+    unsigned char *tail = smem_raw + 2 * STAGE_BYTES + (LX ? 2 * LX_MAX_U * 8 : 0);
     uint64_t *bar = reinterpret_cast<uint64_t *>(tail);                 // [2]
     int64_t *s_base = reinterpret_cast<int64_t *>(tail + 16);           // [2] first staged nonzero
     int32_t *s_nst = reinterpret_cast<int32_t *>(tail + 32);            // [2] staged count, -1 = direct path
+    int32_t *s_ucnt = reinterpret_cast<int32_t *>(tail + 40);           // [2] LX: distinct columns of the staged tile
     double *red = reinterpret_cast<double *>(tail + 64);                // [32]
 
     const int64_t ntiles = (n + rows_per_tile - 1) / rows_per_tile;
@@ -103,14 +118,23 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
         s0 = indptr[r0];
         s1 = indptr[r1];
     };
-    auto issue = [&](int64_t s0, int64_t s1, int stage) {
-        const int64_t base = s0 & ~(int64_t)3, end = (s1 + 3) & ~(int64_t)3;   // 16-byte aligned in both arrays
+    auto issue = [&](int64_t s0, int64_t s1, int stage, int64_t tl) {
+        constexpr int64_t AL = LX ? 7 : 3;                          // 16-byte aligned in every staged array (LX: 2-byte indices)
+        const int64_t base = s0 & ~AL, end = (s1 + AL) & ~AL;
         const int64_t nst = end - base;
-        if (tma_ok && nst <= SPMV_STAGE_ELEMS && end <= nnz_total && nst > 0) {
+        int32_t u0 = 0, ucnt = 0;
+        if (LX) { u0 = lx.uptr[tl]; ucnt = lx.uptr[tl + 1] - u0; }
+        if (tma_ok && nst <= SPMV_STAGE_ELEMS && end <= nnz_total && nst > 0 && (!LX || ucnt > 0)) {
             s_base[stage] = base;
             s_nst[stage] = (int32_t)nst;
             fence_proxy_async();                                   // consumers' generic accesses -> before the refill
-            if (PK) {
+            if (LX) {
+                s_ucnt[stage] = ucnt;
+                mbar_expect_tx(&bar[stage], (uint32_t)(nst * 10 + (int64_t)ucnt * 4));
+                bulk_g2s(stage_vals(stage), values + base, (uint32_t)(nst * 8), &bar[stage]);
+                bulk_g2s(stage_lidx(stage), lx.lidx + base, (uint32_t)(nst * 2), &bar[stage]);
+                bulk_g2s(stage_ucol(stage), lx.ucols + u0, (uint32_t)(ucnt * 4), &bar[stage]);
+            } else if (PK) {
                 mbar_expect_tx(&bar[stage], (uint32_t)(nst * 8));
                 bulk_g2s(stage_vals(stage), packed + base, (uint32_t)(nst * 8), &bar[stage]);
             } else {
@@ -127,17 +151,18 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
     int64_t ns0 = 0, ns1 = 0;                 // thread 0: bounds of the NEXT tile, loaded one iteration early
     if (tid == 0 && tile < ntiles) {
         tile_bounds(tile, ns0, ns1);
-        issue(ns0, ns1, 0);
+        issue(ns0, ns1, 0, tile);
         if (tile + gridDim.x < ntiles) tile_bounds(tile + gridDim.x, ns0, ns1);
     }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
     double dacc = 0.0;
+    bool xs_ready = false;                   // LX: this tile's x entries were already gathered (CTA-uniform)
     for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
         const int stage = k & 1;
         const int64_t next = tile + gridDim.x;
         if (tid == 0 && next < ntiles) {
-            issue(ns0, ns1, stage ^ 1);
+            issue(ns0, ns1, stage ^ 1, next);
             if (next + gridDim.x < ntiles) tile_bounds(next + gridDim.x, ns0, ns1);   // lands during this tile
         }
         const int64_t r0 = tile * rows_per_tile;
@@ -147,10 +172,35 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
         double *vs = stage_vals(stage);
         if (nst >= 0) {
             const int32_t *cs = stage_cols(stage);
-            if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-            else            { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
-            // all of this thread's gathers are issued before any is consumed (U x 2 in flight)
+            if (!(LX && xs_ready)) {
+                if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+                else            { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+            }
             constexpr int U = (SPMV_STAGE_ELEMS + 2 * SPMV_THREADS - 1) / (2 * SPMV_THREADS);
+            if (LX) {
+                // every distinct column of the tile is gathered ONCE (sorted addresses), the products read x from shared
+                const uint16_t *ls = stage_lidx(stage);
+                const double *xs = stage_xs(stage);
+                if (!xs_ready) {                     // first tile of the CTA (or the one before took the direct path)
+                    const int32_t *us = stage_ucol(stage);
+                    const int ucnt = s_ucnt[stage];
+                    for (int j = tid; j < ucnt; j += SPMV_THREADS) stage_xs(stage)[j] = __ldg(x + us[j]);
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = tid * 2 + u * 2 * SPMV_THREADS;
+                    if (e < nst) {
+                        const uint32_t li = *reinterpret_cast<const uint32_t *>(ls + e);
+                        double2 v = *reinterpret_cast<double2 *>(vs + e);
+                        v.x *= xs[li & 0xffffu];
+                        v.y *= xs[li >> 16];
+                        *reinterpret_cast<double2 *>(vs + e) = v;
+                    }
+                }
+                __syncthreads();
+            } else {
+            // all of this thread's gathers are issued before any is consumed (U x 2 in flight)
             int2 c[U];
             double xa[U], xb[U];
 #pragma unroll
@@ -186,6 +236,26 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
                 }
             }
             __syncthreads();
+            }
+        }
+        // LX: the next tile's stage has usually landed by now - start the gathers of its distinct columns, let them fly
+        // during this tile's row sums, store them afterwards.  (s_nst / s_ucnt of the other stage were written by thread 0
+        // before the barrier that ended the product phase.)
+        constexpr int XG = (LX_MAX_U + SPMV_THREADS - 1) / SPMV_THREADS;
+        double xg[XG];
+        bool pre = false;
+        int pre_cnt = 0;
+        if (LX && nst >= 0 && next < ntiles && s_nst[stage ^ 1] >= 0) {
+            if (stage == 0) { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+            else            { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+            const int32_t *us = stage_ucol(stage ^ 1);
+            pre_cnt = s_ucnt[stage ^ 1];
+#pragma unroll
+            for (int q = 0; q < XG; ++q) {
+                const int j = tid + q * SPMV_THREADS;
+                if (j < pre_cnt) xg[q] = __ldg(x + us[j]);
+            }
+            pre = true;
         }
         auto finish = [&](int64_t r, double sum) {
             if (MODE == 1) sum = cvec[r] - sum;
@@ -237,6 +307,17 @@ __global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64
         // The products were written back INTO the TMA stage through the generic proxy: every writing thread orders
         // its own stores before the async-proxy refill (PTX memory model: the fence must come from the writers, a
         // barrier plus thread 0's fence alone is not enough), then the barrier hands the stage back to the producer.
+        if (LX) {
+            if (pre) {
+                double *xn = stage_xs(stage ^ 1);
+#pragma unroll
+                for (int q = 0; q < XG; ++q) {
+                    const int j = tid + q * SPMV_THREADS;
+                    if (j < pre_cnt) xn[j] = xg[q];
+                }
+            }
+            xs_ready = pre;
+        }
         if (nst >= 0) fence_proxy_async();
         __syncthreads();                 // stage fully consumed before thread 0 refills it next iteration
     }
@@ -427,28 +508,44 @@ int spmv_plan_rows(int64_t n, const int64_t *indptr, int *rows_out, cudaStream_t
 namespace {
 
 // PK: `values` points at the packed (fp32 value, column) records and `indices` is unused.
-template <bool DOT, int MODE, bool PK = false>
-int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
-                double *y, const double *c, const double *dot_with, double *dot_out, double *partials,
-                unsigned int *ticket, SmootherArgs sm, cudaStream_t st) {
+template <bool DOT, int MODE, int FMT = FMT_CSR>
+int spmv_launch_fmt(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
+                    double *y, const double *c, const double *dot_with, double *dot_out, double *partials,
+                    unsigned int *ticket, SmootherArgs sm, LxArgs lx, cudaStream_t st) {
     static int ctas_per_sm = 0;                   // per instantiation; the attributes are per device function
-    constexpr int SMEM = PK ? SPMV_SMEM_BYTES_PK : SPMV_SMEM_BYTES;
+    constexpr int SMEM = FMT == FMT_PK ? SPMV_SMEM_BYTES_PK : (FMT == FMT_LX ? SPMV_SMEM_BYTES_LX : SPMV_SMEM_BYTES);
     if (!ctas_per_sm) {
-        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        MWX_CUDA(cudaFuncSetAttribute(k_spmv<DOT, MODE, FMT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int occ = 0;
-        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<DOT, MODE, PK>, SPMV_THREADS, SMEM));
+        MWX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<DOT, MODE, FMT>, SPMV_THREADS, SMEM));
         ctas_per_sm = occ > 0 ? occ : 1;
     }
     // TMA bulk copies need 16-byte aligned global addresses; the kernel aligns offsets, the bases must be too
-    const int tma_ok = (((uintptr_t)values & 15) == 0 && (PK || ((uintptr_t)indices & 15) == 0)) ? 1 : 0;
+    const int tma_ok = (((uintptr_t)values & 15) == 0 && (FMT != FMT_CSR || ((uintptr_t)indices & 15) == 0)) ? 1 : 0;
     // nnz <= -8: a plan from spmv_plan_rows = -(tile height + 4096 * log2(lanes per row))
     const int plan = nnz <= -8 ? (int)(-nnz) : spmv_rows_per_tile(n, nnz);
     const int rows = plan & 4095, lanes = 1 << (plan >> 12);
-    k_spmv<DOT, MODE, PK><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SMEM, st>>>(
-        n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows, lanes);
+    k_spmv<DOT, MODE, FMT><<<spmv_grid(n, ctas_per_sm, rows), SPMV_THREADS, SMEM, st>>>(
+        n, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket, sm, tma_ok, rows, lanes, lx);
     MWX_LAUNCH_CHECK();
     return 0;
+}
+
+// PK: `values` points at the packed records.  lx != nullptr (a plan built for exactly this tile height): the
+// tile-local-column kernel; otherwise the plain one.
+template <bool DOT, int MODE, bool PK = false>
+int spmv_launch(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
+                double *y, const double *c, const double *dot_with, double *dot_out, double *partials,
+                unsigned int *ticket, SmootherArgs sm, cudaStream_t st, const SpmvLX *lx = nullptr) {
+    if (PK)
+        return spmv_launch_fmt<DOT, MODE, FMT_PK>(n, nnz, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket,
+                                                  sm, LxArgs{}, st);
+    if (lx && nnz <= -8 && (int)(-nnz) == lx->plan && lx->n == n)
+        return spmv_launch_fmt<DOT, MODE, FMT_LX>(n, nnz, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket,
+                                                  sm, LxArgs{lx->uptr, lx->ucols, lx->lidx}, st);
+    return spmv_launch_fmt<DOT, MODE, FMT_CSR>(n, nnz, indptr, indices, values, x, y, c, dot_with, dot_out, partials, ticket,
+                                               sm, LxArgs{}, st);
 }
 
 __global__ void k_csr_pack(int64_t nnz, const int32_t *__restrict__ indices, const double *__restrict__ values,
@@ -466,28 +563,28 @@ __global__ void k_csr_pack(int64_t nnz, const int32_t *__restrict__ indices, con
 
 int launch_spmv(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                 const double *x, double *y, const double *dot_with, double *dot_out, double *partials,
-                unsigned int *ticket, cudaStream_t st) {
+                unsigned int *ticket, cudaStream_t st, const SpmvLX *lx) {
     if (dot_with)
         return spmv_launch<true, 0>(n, nnz, indptr, indices, values, x, y, nullptr, dot_with, dot_out, partials, ticket,
-                                    SmootherArgs{}, st);
+                                    SmootherArgs{}, st, lx);
     return spmv_launch<false, 0>(n, nnz, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                 SmootherArgs{}, st);
+                                 SmootherArgs{}, st, lx);
 }
 
 int launch_spmv_axpy(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
-                     const double *x, double *y, const double *c, int sign, cudaStream_t st) {
+                     const double *x, double *y, const double *c, int sign, cudaStream_t st, const SpmvLX *lx) {
     if (sign < 0)
         return spmv_launch<false, 1>(n, nnz, indptr, indices, values, x, y, c, nullptr, nullptr, nullptr, nullptr,
-                                     SmootherArgs{}, st);
+                                     SmootherArgs{}, st, lx);
     return spmv_launch<false, 2>(n, nnz, indptr, indices, values, x, y, c, nullptr, nullptr, nullptr, nullptr,
-                                 SmootherArgs{}, st);
+                                 SmootherArgs{}, st, lx);
 }
 
 int launch_smoother_step(int64_t n, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *values,
                          const double *x_in, double *x_out, const double *b, const double *dinv, double *d,
-                         double c1, double c2, cudaStream_t st) {
+                         double c1, double c2, cudaStream_t st, const SpmvLX *lx) {
     return spmv_launch<false, 3>(n, nnz, indptr, indices, values, x_in, x_out, b, nullptr, nullptr, nullptr, nullptr,
-                                 SmootherArgs{dinv, d, c1, c2}, st);
+                                 SmootherArgs{dinv, d, c1, c2}, st, lx);
 }
 
 // fp32-stored twins: the same kernels reading 8-byte (fp32 value, column) records; vectors and sums stay fp64.
@@ -551,7 +648,7 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
              const double *b, double *x, double tol, int64_t maxiter, const double *dinv,
              PrecondFn precond, void *ctx, double *r, double *z, double *p, double *q,
              int64_t *iters_host, int32_t *info_host, double *resid_host, cudaStream_t st, int max_rechecks,
-             int64_t *first_hit_host, double *xnorm_hist_host, int64_t xnorm_cap) {
+             int64_t *first_hit_host, double *xnorm_hist_host, int64_t xnorm_cap, const SpmvLX *lx) {
     Scratch<CgScalars> sc(st);
     int rechecks = 0;
     int64_t floor_it = 0;
@@ -595,7 +692,7 @@ int cg_solve(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
         }
         k_p_update<<<vec_grid(n), VEC_THREADS, 0, st>>>(n, r, dinv, jacobi ? nullptr : z, p, sc.p, it == 1);
         MWX_LAUNCH_CHECK();
-        rc = launch_spmv(n, nnz, indptr, indices, values, p, q, p, &sc.p->pq, partials.p, &sc.p->ticket[0], st);
+        rc = launch_spmv(n, nnz, indptr, indices, values, p, q, p, &sc.p->pq, partials.p, &sc.p->ticket[0], st, lx);
         if (rc) return rc;
         k_xr_update<<<vec_grid(n), VEC_THREADS, 0, st>>>(n, p, q, x, r, dinv, sc.p, partials.p, jacobi ? 1 : 0);
         MWX_LAUNCH_CHECK();
@@ -796,4 +893,52 @@ extern "C" int mwx_smoother_step_pk(int64_t n, int64_t nnz, const int64_t *indpt
                                     void *stream) {
     if (n <= 0 || !indptr || !packed || !x_in || !x_out || !b || !dinv || !d || x_in == x_out) return MWX_E_BADARG;
     return launch_smoother_step_pk(n, nnz, indptr, (const PackedNz *)packed, x_in, x_out, b, dinv, d, c1, c2, as_stream(stream));
+}
+
+// Tile-local column plan (spmv_lx.cu) for operators held outside a hierarchy - the rank's fine rows in the partitioned
+// solver.  *out = NULL (status 0) when the pattern does not localise; the _lx entry points then must not be used.
+extern "C" int mwx_spmv_lx_create(int64_t n, const int64_t *indptr, const int32_t *indices, int64_t plan, void **out,
+                                  void *stream) {
+    if (!out) return MWX_E_BADARG;
+    *out = nullptr;
+    if (n <= 0 || !indptr || !indices || plan > -8) return MWX_E_BADARG;
+    SpmvLX *p = nullptr;
+    const int rc = spmv_lx_create(n, indptr, indices, (int)(-plan), &p, as_stream(stream));
+    if (rc) return rc;
+    *out = p;
+    return 0;
+}
+
+extern "C" void mwx_spmv_lx_destroy(void *lx) { spmv_lx_destroy((SpmvLX *)lx); }
+
+extern "C" int mwx_spmv_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices, const double *values,
+                           const void *lx, const double *x, double *y, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x || !y) return MWX_E_BADARG;
+    return launch_spmv(n, plan, indptr, indices, values, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream),
+                       (const SpmvLX *)lx);
+}
+
+extern "C" int mwx_spmv_axpy_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices,
+                                const double *values, const void *lx, const double *x, const double *c, int32_t sign,
+                                double *y, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x || !c || !y || sign == 0) return MWX_E_BADARG;
+    return launch_spmv_axpy(n, plan, indptr, indices, values, x, y, c, sign, as_stream(stream), (const SpmvLX *)lx);
+}
+
+extern "C" int mwx_smoother_step_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices,
+                                    const double *values, const void *lx, const double *x_in, double *x_out,
+                                    const double *b, const double *dinv, double *d, double c1, double c2, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x_in || !x_out || !b || !dinv || !d || x_in == x_out)
+        return MWX_E_BADARG;
+    return launch_smoother_step(n, plan, indptr, indices, values, x_in, x_out, b, dinv, d, c1, c2, as_stream(stream),
+                                (const SpmvLX *)lx);
+}
+
+extern "C" int mwx_dcg_spmv_dot_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices,
+                                   const double *values, const void *lx, const double *x_ext, double *q, double *ws,
+                                   void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x_ext || !q || !ws) return MWX_E_BADARG;
+    CgScalars *sc = ws_scalars(ws);
+    return launch_spmv(n, plan, indptr, indices, values, x_ext, q, x_ext, &sc->pq, ws_partials(ws), &sc->ticket[0],
+                       as_stream(stream), (const SpmvLX *)lx);
 }

@@ -105,6 +105,16 @@ def pack_fp32(cols, vals):
     return out
 
 
+def make_lx(op):
+    """Tile-local column plan (csrc/spmv_lx.cu) of a local operator, or None (pattern does not localise / not asked for)."""
+    if os.environ.get('MWX_SPMV_LX', '0') == '0' or op.nloc <= 0 or op.spmv_hint > -8:      # off by default: measured slower (amg.cu)
+        return None
+    h = ctypes.c_void_p()
+    L.check(L.lib().mwx_spmv_lx_create(op.nloc, L.ptr(op.indptr), L.ptr(op.cols), int(op.spmv_hint), ctypes.byref(h),
+                                       L.stream()), 'mwx_spmv_lx_create')
+    return h if h.value else None
+
+
 class LocalOp(HaloPlan):
     """Rows [rlo, rhi) of a global CSR operator (device tensors), columns renumbered to [owned | ghost]."""
 
@@ -115,7 +125,7 @@ class LocalOp(HaloPlan):
         torch = L.require_cuda()
         dev = values.device
         self.rank, self.nloc = rank, rhi - rlo
-        self.bsr, self.pk = None, None
+        self.bsr, self.pk, self.lx = None, None, None
         self.clo, self.ncol = col_offsets[rank], col_offsets[rank + 1] - col_offsets[rank]
         s0, s1 = int(indptr[rlo].item()), int(indptr[rhi].item())
         self.indptr = (indptr[rlo:rhi + 1] - s0).contiguous()
@@ -139,6 +149,8 @@ class LocalOp(HaloPlan):
                                            L.ptr(self.vals), int(block[0]), int(block[1]), 32 if fp32 else 64, ctypes.byref(h),
                                            L.stream()), 'mwx_bsr_create')
             self.bsr = h if h.value else None
+        if self.bsr is None and self.nnz > 0:
+            self.lx = make_lx(self)
         if fp32 and self.bsr is None and self.nnz > 0 and os.environ.get('MWX_PACKED_CSR', '0') != '0':
             self.pk = pack_fp32(self.cols, self.vals)      # scalar operators: measured slower than fp64 CSR (amg.cu), A/B only
 
@@ -146,6 +158,8 @@ class LocalOp(HaloPlan):
         try:
             if getattr(self, 'bsr', None):
                 L.lib().mwx_bsr_destroy(self.bsr)
+            if getattr(self, 'lx', None):
+                L.lib().mwx_spmv_lx_destroy(self.lx)
         except Exception:
             pass
 
@@ -199,6 +213,7 @@ class RankSystem(HaloPlan):
         rows_plan = ctypes.c_int32(0)
         L.check(lib.mwx_spmv_plan(self.nloc, L.ptr(self.indptr), ctypes.byref(rows_plan), st), 'mwx_spmv_plan')
         self.spmv_hint = -int(rows_plan.value)
+        self.lx = make_lx(self)           # never freed explicitly: lives as long as the process's partitioned problem
         # ghost ownership: sorted ghosts are grouped by owner because ownership ranges are contiguous
         self._plan_ghosts(partition.offsets, dev)
 
@@ -699,6 +714,9 @@ class CudaOps:
                    L.ptr(ws), int(first), L.stream())
 
     def spmv_dot(self, p, x_ext, q, ws):
+        if getattr(p, 'lx', None):
+            return self._emit('mwx_dcg_spmv_dot_lx', L.lib().mwx_dcg_spmv_dot_lx, p.nloc, p.spmv_hint, L.ptr(p.indptr),
+                              L.ptr(p.cols), L.ptr(p.vals), p.lx, L.ptr(x_ext), L.ptr(q), L.ptr(ws), L.stream())
         self._emit('mwx_dcg_spmv_dot', L.lib().mwx_dcg_spmv_dot, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_ext), L.ptr(q), L.ptr(ws), L.stream())
 
@@ -716,6 +734,9 @@ class CudaOps:
         if getattr(p, 'pk', None) is not None:
             return self._emit('mwx_spmv_pk', L.lib().mwx_spmv_pk, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.pk),
                               L.ptr(x_ext), L.ptr(y), L.stream())
+        if getattr(p, 'lx', None):
+            return self._emit('mwx_spmv_lx', L.lib().mwx_spmv_lx, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
+                              L.ptr(p.vals), p.lx, L.ptr(x_ext), L.ptr(y), L.stream())
         self._emit('mwx_spmv', L.lib().mwx_spmv, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols), L.ptr(p.vals),
                    L.ptr(x_ext), L.ptr(y), L.stream())
 
@@ -726,6 +747,9 @@ class CudaOps:
         if getattr(p, 'pk', None) is not None:
             return self._emit('mwx_spmv_axpy_pk', L.lib().mwx_spmv_axpy_pk, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.pk),
                               L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
+        if getattr(p, 'lx', None):
+            return self._emit('mwx_spmv_axpy_lx', L.lib().mwx_spmv_axpy_lx, p.nloc, p.spmv_hint, L.ptr(p.indptr),
+                              L.ptr(p.cols), L.ptr(p.vals), p.lx, L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
         self._emit('mwx_spmv_axpy', L.lib().mwx_spmv_axpy, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_ext), L.ptr(c), int(sign), L.ptr(y), L.stream())
 
@@ -741,6 +765,10 @@ class CudaOps:
             return self._emit('mwx_smoother_step_pk', L.lib().mwx_smoother_step_pk, p.nloc, p.spmv_hint, L.ptr(p.indptr),
                               L.ptr(p.pk), L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2),
                               L.stream())
+        if getattr(p, 'lx', None):
+            return self._emit('mwx_smoother_step_lx', L.lib().mwx_smoother_step_lx, p.nloc, p.spmv_hint, L.ptr(p.indptr),
+                              L.ptr(p.cols), L.ptr(p.vals), p.lx, L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d),
+                              float(c1), float(c2), L.stream())
         self._emit('mwx_smoother_step', L.lib().mwx_smoother_step, p.nloc, p.spmv_hint, L.ptr(p.indptr), L.ptr(p.cols),
                    L.ptr(p.vals), L.ptr(x_in), L.ptr(x_out), L.ptr(b), L.ptr(dinv), L.ptr(d), float(c1), float(c2),
                    L.stream())

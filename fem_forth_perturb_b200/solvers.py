@@ -105,15 +105,16 @@ class Reordering:
                 vals = out[2] if out is not None else torch.empty(A.nnz, dtype=torch.float64, device=dev)
             _gather_values(A.d_data, ent['vmap'], vals)
             return DeviceCSR(ent['indptr'], ent['indices'], vals, A.shape, ent['key'], **meta)
-        if out is None:
+        own = out is None                   # buffers allocated here: the cached pattern IS the returned one (later calls hand
+        if out is None:                     # out the same indptr / indices tensors - plans keyed to them stay valid)
             out = (torch.empty(self.n + 1, dtype=torch.int64, device=dev),
                    torch.empty(A.nnz, dtype=torch.int32, device=dev),
                    torch.empty(A.nnz, dtype=torch.float64, device=dev))
         L.check(L.lib().mwx_csr_permute(self.n, L.ptr(A.d_indptr), L.ptr(A.d_indices), L.ptr(A.d_data),
                                         L.ptr(self.perm), L.ptr(self.iperm), L.ptr(out[0]), L.ptr(out[1]),
                                         L.ptr(out[2]), L.stream()), 'mwx_csr_permute')
-        ent = patterns[key] = dict(indptr=out[0].clone(), indices=out[1].clone(), vmap=None, scratch=None,
-                                   key=new_pattern_id())
+        ent = patterns[key] = dict(indptr=out[0] if own else out[0].clone(), indices=out[1] if own else out[1].clone(),
+                                   vmap=None, scratch=None, key=new_pattern_id())
         return DeviceCSR(out[0], out[1], out[2], A.shape, ent['key'], **meta)
 
     def _gather(self, v, idx):

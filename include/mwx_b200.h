@@ -418,6 +418,26 @@ int mwx_smoother_step_pk(int64_t n, int64_t nnz_hint, const int64_t *indptr, con
                          double *x_out, const double *b, const double *dinv, double *d, double c1, double c2,
                          void *stream);
 
+/* Tile-local column plan of a CSR pattern (csrc/spmv_lx.cu; no reference counterpart).  The SpMV kernel is bound by the
+ * L1 wavefronts of its x gathers (11.5 scattered columns per Morley row), not by DRAM; the rows of one tile share their
+ * columns, so the plan lists each tile's DISTINCT columns once (sorted) and gives every nonzero a 2-byte index into that
+ * list: the kernel gathers each distinct x entry once into shared memory.  MEASURED SLOWER than the plain kernel on
+ * B200 (3.15 against 2.73 ms per smoother step at 67 M rows: fewer wavefronts and bytes, but one more barrier per tile),
+ * so nothing uses it unless MWX_SPMV_LX=1; results are bit-identical.  plan = the (negative) value mwx_spmv_plan
+ * returned for this matrix.  *out = NULL (status 0) when some tile has more than 768 distinct columns: keep the plain
+ * entry points.  The _lx entry points are mwx_spmv / mwx_spmv_axpy / mwx_smoother_step / mwx_dcg_spmv_dot with the plan. */
+int mwx_spmv_lx_create(int64_t n, const int64_t *indptr, const int32_t *indices, int64_t plan, void **out, void *stream);
+void mwx_spmv_lx_destroy(void *lx);
+int mwx_spmv_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices, const double *values,
+                const void *lx, const double *x, double *y, void *stream);
+int mwx_spmv_axpy_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices, const double *values,
+                     const void *lx, const double *x, const double *c, int32_t sign, double *y, void *stream);
+int mwx_smoother_step_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices, const double *values,
+                         const void *lx, const double *x_in, double *x_out, const double *b, const double *dinv,
+                         double *d, double c1, double c2, void *stream);
+int mwx_dcg_spmv_dot_lx(int64_t n, int64_t plan, const int64_t *indptr, const int32_t *indices, const double *values,
+                        const void *lx, const double *x_ext, double *q, double *ws, void *stream);
+
 /* Block-CSR twin of a CSR operator whose nonzeros come in br x bc blocks (3x3, 1x3, 3x1: the coarse operators of a
  * smoothed-aggregation hierarchy on three candidates); *out = NULL (status 0) when the operator is not blocked that way.
  * Used for the row blocks of the partitioned V-cycle; inside a single-GPU hierarchy the library builds them itself.
