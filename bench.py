@@ -67,6 +67,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first(self, timeout=8.0):
+        """Block until the first sample has arrived (or the sampler could not start): the sampling then runs DURING the
+        timed region, but nvidia-smi's start-up - seconds of NVML initialisation that can stall CUDA calls - does not."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def _read(self):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in self.proc.stdout:
@@ -402,6 +409,7 @@ def run_single(args, torch, F, L, dev, local):
     def step(e2e, mode):
         """One pass of the hot path.  Returns per-phase device milliseconds and the iteration count."""
         ml = mls[mode]
+        t_step = time.perf_counter()
         marks = [ev() for _ in range(8)]
         if e2e:
             gm.d_pxy.copy_(p_host, non_blocking=True)
@@ -436,7 +444,7 @@ def run_single(args, torch, F, L, dev, local):
         torch.cuda.synchronize()
         ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(7)]
         return dict(asm=ms[0], condense=ms[1], spmv_skfem=ms[3], reorder=ms[4], spmv=ms[5], pcg=ms[6], its=its,
-                    info=info, resid=resid, x=x)
+                    info=info, resid=resid, x=x, wall_ms=(time.perf_counter() - t_step) * 1e3)
 
     def timed(e2e, mode, steps, warmup):
         for _ in range(warmup):
@@ -454,6 +462,7 @@ def run_single(args, torch, F, L, dev, local):
 
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first()          # nvidia-smi's start-up (NVML initialisation) must not land inside the timed steps
     total_ms, rs = timed(False, args.mode, args.steps, args.warmup)
     clocks = sampler.stop()
     e2e_ms, rs_e2e = timed(True, args.mode, args.steps, 1)
@@ -473,6 +482,8 @@ def run_single(args, torch, F, L, dev, local):
                 'value_incl_amg_setup_mdof_s': N / (ms_step_ * 1e-3 + setup) / 1e6,
                 'pcg_iters': its, 'pcg_info': rr[-1]['info'], 'pcg_s_per_solve': mean('pcg', rr) * 1e-3,
                 'pcg_ms_per_iter': mean('pcg', rr) / max(its, 1),
+                'step_wall_ms': [round(r['wall_ms'], 1) for r in rr], 'step_pcg_ms': [round(r['pcg'], 1) for r in rr],
+                'e2e_step_wall_ms': [round(r['wall_ms'], 1) for r in rs_e2e] if mode == args.mode else None,
                 'amg_setup_s': setup, 'amg_setup_where': ml.setup, 'amg_host_setup_s': ml.setup_host_seconds,
                 'amg_device_setup_s': ml.setup_device_seconds, 'amg_upload_s': ml.upload_seconds,
                 'amg_reorder_s': ml.reorder_seconds, 'levels': ml.level_sizes(),
@@ -857,6 +868,7 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     total_ms, rs = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _ = timed(True, args.steps, 1)

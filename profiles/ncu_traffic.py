@@ -4,7 +4,7 @@ For every kernel of interest the LAST captured launch gives dram__bytes_read.sum
 records the sha256 of the kernel's source file, so that bench.py reports null once the source has changed."""
 import csv, hashlib, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = {'k_spmv<0, 0>': ('k_spmv', 'fem_forth_perturb_b200/csrc/krylov.cu'), 'k_spmv<false, 0>': ('k_spmv', 'fem_forth_perturb_b200/csrc/krylov.cu'),
+KERNELS = {'k_spmv<0, 0, 0>': ('k_spmv', 'fem_forth_perturb_b200/csrc/krylov.cu'), 'k_spmv<false, 0, 0>': ('k_spmv', 'fem_forth_perturb_b200/csrc/krylov.cu'),
            'k_assemble_morley_tiles': ('assembly', 'fem_forth_perturb_b200/csrc/asm_tiles.cu')}
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
 rep, level = sys.argv[1], int(sys.argv[2])
