@@ -220,6 +220,20 @@ def main():
     run_single(args, torch, F, L, dev, local)
 
 
+def vcycle_launches(nlev, revisit=()):
+    """Kernel launches of one AMG cycle on `nlev` levels: 7 per visit of a smoothed level (first smoother step, one
+    smoother SpMV, residual, restriction, prolongation, two smoother SpMVs), one dense GEMV per visit of the coarsest
+    level, and residual + accumulate for every second visit of a level in `revisit` (gamma = 2 there).  Matches the ncu
+    launch list (profiles/r02_launches_pcg_level12_sa.txt: 134 + the 4 CG kernels)."""
+    visits, total = 1, 0
+    for l in range(nlev - 1):
+        if l in revisit:
+            total += 2 * visits           # per visit of the parent: residual for the second visit + accumulate
+            visits *= 2
+        total += 7 * visits
+    return total + visits
+
+
 def kernel_traffic(kernel, level):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
     (profiles/ncu_traffic.json, written by profiles/ncu_summary.py).  An entry is keyed to the sha256 of the kernel's
@@ -513,6 +527,7 @@ def run_single(args, torch, F, L, dev, local):
 
     # one hierarchy at a time: release the headline hierarchy, time the reference-shaped call, then the spec mode
     ml_levels, ml_reordered = mls[args.mode].levels, mls[args.mode].reordering is not None
+    ml_sizes = mls[args.mode].level_sizes()
     mls.pop(args.mode)
     torch.cuda.empty_cache()
     # the reference-shaped call: solver_iter_mgcg(tol)(A, b) rebuilds the hierarchy inside every call
@@ -559,7 +574,9 @@ def run_single(args, torch, F, L, dev, local):
     asm_gbs = asm_bytes / (mean('asm', rs) * 1e-3) / 1e9
     iters = rs[-1]['its']
     nlev = ml_levels
-    per_vcycle = (nlev - 1) * 7 + 1      # per level: first step, 1 smoother SpMV, residual, restrict, prolong, 2 smoother SpMVs; + coarse gemv
+    sizes_main = ml_sizes
+    revisit_main = [l for l in range(2, nlev - 1) if sizes_main and sizes_main[l] >= 10000] if (args.mode == 'sa' and os.environ.get('MWX_SA_CYCLE', 'auto') != 'v') else []
+    per_vcycle = vcycle_launches(nlev, revisit_main)
     gpu_launches = int(args.steps * (2 + 1 + 1 + 1 + 3 + iters * (4 + per_vcycle)))
     level_main = args.level
     numbering = 'hilbert (solver-internal)' if ml_reordered else 'skfem'
@@ -844,13 +861,18 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
         marks[2].record()
         ops.spmv(p, xs_ext, ysp)
         marks[3].record()
+        flush.zero_()                      # a second SpMV sample per step (see `spmv.note`: one outlier is dropped)
+        extra = (ev(), ev())
+        extra[0].record()
+        ops.spmv(p, xs_ext, ysp)
+        extra[1].record()
         xs, its, info, resid = D.dist_pcg([p], comm, [bd], tol=TOL, maxiter=3000, precond='amg', amg=ml, ops=ops)
         marks[4].record()
         if e2e:
             x_host.copy_(xs[0], non_blocking=True)
         torch.cuda.synchronize()
         return dict(asm=marks[0].elapsed_time(marks[1]), spmv=marks[2].elapsed_time(marks[3]),
-                    pcg=marks[3].elapsed_time(marks[4]), its=its, info=info, x=xs[0])
+                    spmv2=extra[0].elapsed_time(extra[1]), pcg=extra[1].elapsed_time(marks[4]), its=its, info=info, x=xs[0])
 
     def timed(e2e, steps, warmup):
         for _ in range(warmup):
@@ -875,7 +897,9 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     err2 = torch.stack((torch.sum((rs[-1]['x'] - xs_ext[:p.nloc]) ** 2), torch.sum(xs_ext[:p.nloc] ** 2)))
     dist.all_reduce(err2)
     # per-rank maxima of the phases (device events), reduced with MAX
-    ph = torch.tensor([np.mean([r['asm'] for r in rs]), np.mean([r['spmv'] for r in rs]), np.mean([r['pcg'] for r in rs]),
+    sp_samples = sorted([r['spmv'] for r in rs] + [r['spmv2'] for r in rs])
+    sp_mean = float(np.mean(sp_samples[:-1]))         # 2 samples per step; the largest one is dropped (clock-sampler hiccups)
+    ph = torch.tensor([np.mean([r['asm'] for r in rs]), sp_mean, np.mean([r['pcg'] for r in rs]),
                        float(p.nnz), float(p.nloc), float(p.nghost), float(nt) / world], dtype=torch.float64, device=dev)
     phmax = ph.clone(); dist.all_reduce(phmax, op=dist.ReduceOp.MAX)
     phsum = ph.clone(); dist.all_reduce(phsum)
@@ -889,7 +913,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     spmv_bytes_rank = 12 * float(phmax[3]) + 20 * nloc_max
     spmv_gbs_rank = spmv_bytes_rank / (float(phmax[1]) * 1e-3) / 1e9
     nlev = ml.nlevels
-    per_vcycle = (nlev - 1) * 7 + 1
+    # cycle kernels + per distributed level 5 halo pushes (2 more per revisit) + all-gather / copies around the tail; a lower bound
+    per_vcycle = vcycle_launches(nlev, getattr(ml, 'revisit', ())) + 5 * ml.lsw + 3
     line = {
         'metric': 'hot_path_MDOF_per_s', 'value': value, 'unit': 'MDOF/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
@@ -913,7 +938,8 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
                 'block_csr_operators': sum(1 for lv in ml.levels for k in 'APR' for op in lv[k] if getattr(op, 'bsr', None)),
                 'cuda_graph': bool(getattr(comm, 'graphable', False)) and os.environ.get('MWX_DIST_GRAPH', '1') != '0'},
         'spmv': {'ms': float(phmax[1]), 'gbs_per_gpu': spmv_gbs_rank, 'frac_of_peak': spmv_gbs_rank / peak,
-                 'note': 'local block of the slowest rank, halo not included'},
+                 'note': 'local block of the slowest rank, halo not included; two samples per step (256 MiB written before each), '
+                         'mean of all but the largest one'},
         'partition': {'rows_max': int(nloc_max), 'ghosts_max': int(phmax[5]), 'nnz_total': int(nnzc_glob)},
         'setup_s': {'mesh_refine_pattern': t_mesh, 'partition_plan': t_part, 'amg_global_setup_and_distribution': t_amg,
                     'amg_setup_where': ('every rank builds the global hierarchy on its own GPU (device setup, bit-identical)' if amg_mode == 'sa' else 'root host, broadcast'),
