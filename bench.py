@@ -810,7 +810,13 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     t0 = time.perf_counter()
     # halo exchange: pack-and-push kernels into the neighbours' peer memory over NVLink (MWX_HALO=nccl: send/recv)
     halo_kind = os.environ.get('MWX_HALO', 'peer')
-    comm = {'nccl': D.TorchDistComm, 'symm': D.SymmMemComm, 'peer': D.PeerComm}[halo_kind]()
+    try:
+        comm = {'nccl': D.TorchDistComm, 'symm': D.SymmMemComm, 'peer': D.PeerComm}[halo_kind]()
+    except Exception as exc:               # no symmetric memory / peer mapping on this box: NCCL send/recv + all-reduce (stated in `config`)
+        if halo_kind == 'nccl':
+            raise
+        sys.stderr.write(f'[bench] {halo_kind} communicator unavailable ({exc!r}); falling back to NCCL\n')
+        halo_kind, comm = 'nccl', D.TorchDistComm()
     prob = D.PartitionedProblem(basis, Dset, comm).assemble(form)
     (p,) = prob.parts
     torch.cuda.synchronize()

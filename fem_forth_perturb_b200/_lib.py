@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmwx_b200.so')
+LIB_PATH = os.environ.get('MWX_LIB_PATH') or os.path.join(_HERE, 'libmwx_b200.so')     # MWX_LIB_PATH: a variant build (kernel tuning runs)
 
 _lib = None
 

@@ -47,7 +47,16 @@ __device__ __forceinline__ bool fold_partials(double v_thread0, double *partials
 }
 
 // Shared-memory plan of the SpMV CTA: two stages of (values, column indices) filled by TMA.
-constexpr int SPMV_STAGE_ELEMS = SPMV_ROWS * 20 + 8;                 // staged nonzeros per stage (<= 20 per row)
+#ifndef MWX_SPMV_STAGE_ROWS
+// Stage capacity (in 20-nonzero rows) and CTAs per SM, tuned together (profiles/r02_spmv_stage_tuning.txt, 67 M rows):
+// 128 rows x 3 CTAs (80 registers) 2.16 ms; 112 x 4 (64 registers, the same 192-row tiles) 2.02 ms; 96 x 4 2.06; 80 x 4 2.27;
+// 64 x 5 2.42; 160 x 2 2.34 - the kernel is latency-bound, one more resident CTA pays as long as the tile height stays.
+#define MWX_SPMV_STAGE_ROWS 112
+#endif
+#ifndef MWX_SPMV_MINB
+#define MWX_SPMV_MINB 4
+#endif
+constexpr int SPMV_STAGE_ELEMS = MWX_SPMV_STAGE_ROWS * 20 + 8;       // staged nonzeros per stage (<= 20 per row)
 constexpr int SPMV_STAGE_BYTES = SPMV_STAGE_ELEMS * 12;             // 8 B value + 4 B column
 constexpr int SPMV_SMEM_BYTES = 2 * SPMV_STAGE_BYTES + 64 + 32 * 8; // + barriers/meta + reduction scratch
 // PK (fp32-stored operator, see PackedNz in krylov.cuh): one 8-byte (value, column) record per nonzero; the fp64
@@ -74,7 +83,7 @@ struct SmootherArgs { const double *dinv; double *d; double c1, c2; };
 // a thread's gathers are in flight together), write the products back in place, and one thread per
 // row adds its products in CSR order.
 template <bool DOT, int MODE, int FMT = FMT_CSR>
-__global__ void __launch_bounds__(SPMV_THREADS, 3) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(SPMV_THREADS, MWX_SPMV_MINB) k_spmv(int64_t n, const int64_t *__restrict__ indptr,
                                                     const int32_t *__restrict__ indices,
                                                     const double *__restrict__ values,
                                                     const double *__restrict__ x, double *y,
