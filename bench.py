@@ -60,7 +60,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), f'--query-gpu={q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '500'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -420,11 +420,19 @@ def run_single(args, torch, F, L, dev, local):
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)     # 256 MiB > 126 MB L2
     hints = {}
 
+    # Events are created (and recorded once) up front and reused: nothing that takes the driver's context lock
+    # (cudaEventCreate / Destroy, cudaMalloc of a fresh output block) is left at the step boundaries, where the
+    # nvidia-smi sampler polling the same driver was seen to stall such calls for 0.3-0.5 s on some boxes.
+    step_events, region_events = [ev() for _ in range(8)], [ev(), ev()]      # a step synchronises and reads its events before it returns
+    for e in step_events + region_events:
+        e.record()
+    torch.cuda.synchronize()
+
     def step(e2e, mode):
         """One pass of the hot path.  Returns per-phase device milliseconds and the iteration count."""
         ml = mls[mode]
         t_step = time.perf_counter()
-        marks = [ev() for _ in range(8)]
+        marks = step_events
         if e2e:
             gm.d_pxy.copy_(p_host, non_blocking=True)
             gm.d_t.copy_(t_host, non_blocking=True)
@@ -464,9 +472,14 @@ def run_single(args, torch, F, L, dev, local):
         for _ in range(warmup):
             step(e2e, mode)
         torch.cuda.synchronize()
-        e0, e1 = ev(), ev()
+        e0, e1 = region_events
         e0.record()
-        rs = [step(e2e, mode) for _ in range(steps)]
+        rs = []
+        for i in range(steps):
+            r = step(e2e, mode)
+            if i < steps - 1:
+                r['x'] = None                      # only the last iterate is looked at: its block is reused, no new cudaMalloc per step
+            rs.append(r)
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), rs
@@ -851,8 +864,13 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    step_events, region_events = [ev() for _ in range(7)], [ev(), ev()]      # created once, reused (see run_single)
+    for e in step_events + region_events:
+        e.record()
+    torch.cuda.synchronize()
+
     def step(e2e):
-        marks = [ev() for _ in range(5)]
+        marks = step_events[:5]
         if e2e:
             gm.d_pxy.copy_(p_host, non_blocking=True)
             if p.tile_plan is None:                   # the tiled kernel reads the connectivity from its plan, not from t
@@ -868,7 +886,7 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
         ops.spmv(p, xs_ext, ysp)
         marks[3].record()
         flush.zero_()                      # a second SpMV sample per step (see `spmv.note`: one outlier is dropped)
-        extra = (ev(), ev())
+        extra = step_events[5:7]
         extra[0].record()
         ops.spmv(p, xs_ext, ysp)
         extra[1].record()
@@ -884,9 +902,14 @@ def run_partitioned(args, torch, dist, F, L, dev, rank, world, local):
         for _ in range(warmup):
             step(e2e)
         sync_all()
-        e0, e1 = ev(), ev()
+        e0, e1 = region_events
         e0.record()
-        rs = [step(e2e) for _ in range(steps)]
+        rs = []
+        for i in range(steps):
+            r = step(e2e)
+            if i < steps - 1:
+                r['x'] = None                      # only the last iterate is looked at afterwards
+            rs.append(r)
         e1.record()
         sync_all()
         tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
