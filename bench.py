@@ -56,6 +56,8 @@ class ClockSampler:
         self.gpu_index = gpu_index
 
     def start(self):
+        if os.environ.get('MWX_BENCH_NO_SAMPLER'):          # A/B switch: is a stall in the timed region the sampler's doing?
+            return
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
@@ -439,11 +441,14 @@ def run_single(args, torch, F, L, dev, local):
             bd = b_host.to(dev, non_blocking=True)
         else:
             bd = b
+        host_t = [time.perf_counter()]
         marks[0].record()
         K = F.asm_gpu(form, basis, out=vals)
         marks[1].record()
+        host_t.append(time.perf_counter())
         Kcs, _ = plan.apply(K, values_out=vals_c)
         marks[2].record()
+        host_t.append(time.perf_counter())
         if 'kc' not in hints:                           # tile plans depend on the pattern only: once, outside the marks
             hints['kc'] = Kcs.spmv_hint()
         flush.zero_()                                   # evict the operator from L2 before the SpMV sample
@@ -459,14 +464,18 @@ def run_single(args, torch, F, L, dev, local):
         L.check(L.lib().mwx_spmv(n, hints['ks'], L.ptr(Ks.d_indptr), L.ptr(Ks.d_indices), L.ptr(Ks.d_data), L.ptr(xstar),
                                  L.ptr(ysp), L.stream()), 'mwx_spmv')
         marks[6].record()
+        host_t.append(time.perf_counter())
         x, its, info, resid = F.pcg(Kcs, bd, TOL, 2000, amg=ml)
         marks[7].record()
+        host_t.append(time.perf_counter())
         if e2e:
             x_host.copy_(x, non_blocking=True)
         torch.cuda.synchronize()
+        host_t.append(time.perf_counter())
         ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(7)]
         return dict(asm=ms[0], condense=ms[1], spmv_skfem=ms[3], reorder=ms[4], spmv=ms[5], pcg=ms[6], its=its,
-                    info=info, resid=resid, x=x, wall_ms=(time.perf_counter() - t_step) * 1e3)
+                    info=info, resid=resid, x=x, wall_ms=(time.perf_counter() - t_step) * 1e3,
+                    host_ms=[round((host_t[0] - t_step) * 1e3, 1)] + [round((b_ - a_) * 1e3, 1) for a_, b_ in zip(host_t[:-1], host_t[1:])])
 
     def timed(e2e, mode, steps, warmup):
         for _ in range(warmup):
@@ -510,6 +519,7 @@ def run_single(args, torch, F, L, dev, local):
                 'pcg_iters': its, 'pcg_info': rr[-1]['info'], 'pcg_s_per_solve': mean('pcg', rr) * 1e-3,
                 'pcg_ms_per_iter': mean('pcg', rr) / max(its, 1),
                 'step_wall_ms': [round(r['wall_ms'], 1) for r in rr], 'step_pcg_ms': [round(r['pcg'], 1) for r in rr],
+                'step_host_ms_[pre,asm,condense,spmv+reorder,pcg,sync]': [r['host_ms'] for r in rr],
                 'e2e_step_wall_ms': [round(r['wall_ms'], 1) for r in rs_e2e] if mode == args.mode else None,
                 'amg_setup_s': setup, 'amg_setup_where': ml.setup, 'amg_host_setup_s': ml.setup_host_seconds,
                 'amg_device_setup_s': ml.setup_device_seconds, 'amg_upload_s': ml.upload_seconds,

@@ -30,13 +30,22 @@ int exclusive_scan_i32_to_i64(const int32_t *in, int64_t n, int64_t *out, cudaSt
 // int32 output variant (out[0..n]); total must fit in int32.
 int exclusive_scan_i32_to_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
 
+// The default memory pool hands freed blocks back to the OS at every synchronisation (release threshold 0): a 268 MB
+// scratch array freed inside a step was unmapped at the step's final device synchronisation and mapped again in the next
+// step - hundreds of milliseconds on some (virtualised) boxes.  Once per process the threshold is raised so that scratch
+// memory stays in the pool.
+void keep_pool_memory();
+
 // Stream-ordered scratch buffer with RAII release.
 template <typename T>
 struct Scratch {
     T *p = nullptr;
     cudaStream_t st;
     explicit Scratch(cudaStream_t s) : st(s) {}
-    cudaError_t alloc(size_t n) { return cudaMallocAsync((void **)&p, (n ? n : 1) * sizeof(T), st); }
+    cudaError_t alloc(size_t n) {
+        keep_pool_memory();
+        return cudaMallocAsync((void **)&p, (n ? n : 1) * sizeof(T), st);
+    }
     ~Scratch() { if (p) cudaFreeAsync(p, st); }
     Scratch(const Scratch &) = delete;
     Scratch &operator=(const Scratch &) = delete;

@@ -105,6 +105,19 @@ int exclusive_scan_i32_to_i32(const int32_t *in, int64_t n, int32_t *out, cudaSt
     return exclusive_scan_impl<int32_t, int32_t>(in, n, out, st);
 }
 
+void keep_pool_memory() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~(uint64_t)0;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 int sm_count() {
     static int cached = 0;
     if (!cached) {
