@@ -1017,7 +1017,7 @@ class DistAMG:
     residual is all-gathered and every rank runs the remaining levels redundantly with the single-GPU V-cycle.
     Smoother = Chebyshev (fast mode); iteration counts match the single-GPU fast mode to round-off."""
 
-    def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=500000,
+    def __init__(self, parts, comm, global_matrix, mode='chebyshev', degree=2, ratio=10.0, switch_rows=None,
                  max_levels=10, ops=None, setup='device'):
         """mode 'chebyshev': the reference's Ruge-Stueben hierarchy; 'sa': smoothed aggregation (the global matrix
         must carry near-nullspace candidates, see AMGHierarchy).  Chebyshev smoothing either way."""
@@ -1026,6 +1026,8 @@ class DistAMG:
         from .assembly import DeviceCSR
         if mode not in ('chebyshev', 'sa'):
             raise NotImplementedError("the partitioned V-cycle implements the Chebyshev smoother (modes 'chebyshev', 'sa')")
+        if switch_rows is None:
+            switch_rows = int(os.environ.get('MWX_DIST_SWITCH_ROWS', 500000))
         self.parts, self.comm, self.ops = parts, comm, ops or CudaOps()
         self.degree, self.ratio = int(degree), float(ratio)
         self._programs, self._tail_out = {}, None
@@ -1134,7 +1136,8 @@ class DistAMG:
             sizes = [o[-1] for o in offs[:lsw]] + self.tail.level_sizes()
             min_rows = int(os.environ.get('MWX_SA_CYCLE_MIN_ROWS', 10000))
             last = max([g for g in range(2, len(sizes) - 1) if sizes[g] >= min_rows], default=0)
-            self.revisit = tuple(range(2 if everywhere else max(2, lsw), last + 1))
+            first_small = int(os.environ.get('MWX_SA_CYCLE_FIRST_SMALL', max(2, lsw)))
+            self.revisit = tuple(range(2 if everywhere else max(2, first_small), last + 1))
             self.tail.set_cycle(1, 0)
             if last - lsw >= 1 and self.revisit:
                 self.tail.set_cycle(2, last - lsw, first=max(1, 2 - lsw))
