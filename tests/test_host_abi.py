@@ -28,6 +28,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.mwx_version() >= 100
 
 
+def test_ctypes_signatures_have_the_header_arity():
+    """Every declaration of include/mwx_b200.h has as many parameters as its ctypes signature (a changed C signature
+    that the Python side missed would otherwise only show up as garbage arguments on the GPU)."""
+    txt = open(os.path.join(ROOT, 'include', 'mwx_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)                      # comments contain commas and parentheses
+    decls = re.findall(r'^(?:int|void)\s+(mwx_\w+)\s*\(([^;]*?)\)\s*;', txt, flags=re.M | re.S)
+    assert len(decls) >= 100
+    for name, args in decls:
+        args = args.strip()
+        n = 0 if args in ('', 'void') else args.count(',') + 1
+        assert n == len(L._SIGNATURES[name]), (name, n, len(L._SIGNATURES[name]))
+
+
+def test_bench_launch_count_matches_the_profiled_cycle():
+    """bench.py's `gpu_launches` claim: the cycle-shape formula reproduces the ncu launch list of one iteration
+    (profiles/r02_launches_pcg_level12_sa.txt: 138 launches = 134 of the cycle + 4 CG kernels)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.vcycle_launches(6, [2, 3, 4]) == 134
+    assert bench.vcycle_launches(6, []) == 5 * 7 + 1
+    assert bench.vcycle_launches(2, []) == 8
+    listing = open(os.path.join(ROOT, 'profiles', 'r02_launches_pcg_level12_sa.txt')).read()
+    assert 'launches 138' in listing
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
