@@ -253,7 +253,7 @@ def kernel_traffic(kernel, level):
         return None
 
 
-def ex1_pipeline(torch, F, gm, ubasis, plan, K2, eps, solve_u, w_mode, tol):
+def ex1_pipeline(torch, F, gm, ubasis, plan, K2, eps, solve_u, w_mode, tol, refine_u=None):
     """The reference's solve_problem1 (ref main/example1/run.py:182-222, w in P1 as in the golden 8-level log) with
     every array on the device: K1 = asm(laplace), f1 = asm(f_load) -> w_h; f2 = asm(wv_load) * w_h; condense; u_h.
     Loads and the exact solution are the 'ex1' data of problems.py evaluated by the kernels.
@@ -290,6 +290,22 @@ def ex1_pipeline(torch, F, gm, ubasis, plan, K2, eps, solve_u, w_mode, tol):
                      'true_rel_residual': float(torch.linalg.norm(bc - Kc.dot(x))) / bn, 's_per_solve': dt,
                      'L2': L2, 'H1': L2 + D1, 'H2': L2 + D1 + D2, 'energy': float(np.sqrt(eps ** 2 * D2 ** 2 + D1 ** 2))}
         sols[name] = x
+        if refine_u is not None and its < 500:
+            # mixed-precision iterative refinement (residual in double-double, solvers.refine): the forward error leaves the
+            # cond(A) * eps floor of the plain fp64 solve, so the discretisation error - and its order - shows on the finest levels
+            log = []
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            xr = refine_u(name, Kc, bc, x, log)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            uh.zero_()
+            uh[I_dev] = xr
+            L2, D1, D2 = F.morley_error_norms(ubasis, uh, problem=prob)
+            out[name]['refined'] = {'steps': log, 's': dt, 'L2': L2, 'H1': L2 + D1, 'H2': L2 + D1 + D2,
+                                    'energy': float(np.sqrt(eps ** 2 * D2 ** 2 + D1 ** 2)),
+                                    'rel_change_of_solution': float(torch.linalg.norm(xr - x) / torch.linalg.norm(xr))}
+            sols[name + '_refined'] = xr
     return out, sols
 
 
@@ -316,13 +332,18 @@ def ex1_level(torch, F, level, eps, tol, modes, maxiter, setup=None):
             x, its, info, _ = F.pcg(Kc_, bc_, tol, maxiter[mode], amg=mls[mode], max_rechecks=2, monitor=mon)
             return x, its, info, mon.get('first_hit')
         return fn
+    def refine_u(mode, Kc_, bc_, x, log):
+        return F.refine(Kc_, bc_, x, steps=2, tol=tol, maxiter=maxiter[mode], amg=mls[mode], log=log)
     res, sols = ex1_pipeline(torch, F, gm, ub, plan, K2, eps, {m: solver(m) for m in modes if m in mls},
-                             modes[0] if modes[0] in ('sa', 'chebyshev') else 'chebyshev', tol)
+                             modes[0] if modes[0] in ('sa', 'chebyshev') else 'chebyshev', tol, refine_u=refine_u)
     res['dofs'] = ub.N
     names = [m for m in modes if m in sols]
     if len(names) == 2:
         a, b2 = sols[names[0]], sols[names[1]]
         res[f'rel_l2_diff_{names[0]}_vs_{names[1]}'] = float(torch.linalg.norm(a - b2) / torch.linalg.norm(b2))
+        ra, rb = sols.get(names[0] + '_refined'), sols.get(names[1] + '_refined')
+        if ra is not None and rb is not None:
+            res[f'rel_l2_diff_refined_{names[0]}_vs_{names[1]}'] = float(torch.linalg.norm(ra - rb) / torch.linalg.norm(rb))
     return res
 
 
@@ -643,6 +664,9 @@ def run_single(args, torch, F, L, dev, local):
                 if isinstance(hi.get(name), dict) and isinstance(lo.get(name), dict):
                     hi[name]['orders_vs_level_below'] = {k: float(-np.log2(hi[name][k] / lo[name][k]))
                                                          for k in ('L2', 'H1', 'H2', 'energy')}
+                    if isinstance(hi[name].get('refined'), dict) and isinstance(lo[name].get('refined'), dict):
+                        hi[name]['refined']['orders_vs_level_below'] = {
+                            k: float(-np.log2(hi[name]['refined'][k] / lo[name]['refined'][k])) for k in ('L2', 'H1', 'H2', 'energy')}
     if not args.no_same_config:
         try:
             same_cfg = {'gpu': same_config_level8(torch, F, L, args.ref_level, TOL)}

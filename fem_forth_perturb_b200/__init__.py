@@ -17,10 +17,10 @@ from .assembly import (asm_gpu, asm, DeviceCSR, MixedAction, morley_error_norms,
 from .problems import Problem                                            # noqa: F401
 from .solvers import (solver_iter_krylov, solver_iter_krylov_iter,       # noqa: F401
                       solver_iter_pcg, solver_iter_mgcg, solver_iter_mgcg_iter, solver_iter_pyamg,
-                      build_pc_diag, solve, condense, CondensePlan, AMGHierarchy, pcg)
+                      build_pc_diag, solve, condense, CondensePlan, AMGHierarchy, pcg, refine, residual_dd)
 
 __all__ = ['MeshTri', 'ElementTriMorley', 'ElementTriP1', 'ElementTriP2', 'InteriorBasis', 'FacetBasis',
            'a_load', 'b_load', 'penalty_1', 'penalty_2', 'penalty_3', 'laplace', 'wv_load', 'LinearForm', 'asm_gpu', 'asm',
            'DeviceCSR', 'MixedAction', 'morley_error_norms', 'morley_facet_pnv', 'morley_nested_error_norms', 'project', 'mass',
            'solver_iter_krylov', 'solver_iter_krylov_iter', 'solver_iter_pcg', 'solver_iter_mgcg',
-           'solver_iter_mgcg_iter', 'solver_iter_pyamg', 'build_pc_diag', 'solve', 'condense', 'CondensePlan', 'AMGHierarchy', 'pcg', 'MwxError', 'Problem']
+           'solver_iter_mgcg_iter', 'solver_iter_pyamg', 'build_pc_diag', 'solve', 'condense', 'CondensePlan', 'AMGHierarchy', 'pcg', 'refine', 'residual_dd', 'MwxError', 'Problem']

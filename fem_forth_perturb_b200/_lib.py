@@ -54,6 +54,7 @@ _SIGNATURES = {
     'mwx_halo_push': [i64, i32, vp, vp, vp, vp, vp],
     'mwx_bsr_create': [i64, i64, i64, vp, vp, vp, i32, i32, i32, ctypes.POINTER(vp), vp],
     'mwx_amg_set_storage': [vp, i32, vp],
+    'mwx_residual_dd': [i64, vp, vp, vp, vp, vp, vp, vp],
     'mwx_spmv_lx_create': [i64, vp, vp, i64, ctypes.POINTER(vp), vp],
     'mwx_spmv_lx_destroy': [vp],
     'mwx_spmv_lx': [i64, i64, vp, vp, vp, vp, vp, vp, vp],

@@ -437,6 +437,31 @@ __global__ void k_csr_diagonal(int64_t n, const int64_t *__restrict__ indptr,
     diag[r] = invert ? 1.0 / d : d;
 }
 
+// r = b - A x with every row accumulated in double-double (error-free products by FMA, two-sum accumulation) and
+// rounded once at the end: the residual a mixed-precision iterative refinement needs.  On the finest meshes the fp64
+// residual carries a rounding error eps ||A|| ||x|| that is LARGER than tol ||b|| (condition number ~1e10), so neither
+// the stopping rule nor the forward error can go below ~1e-6 without it.  One thread per row; not a hot kernel.
+__global__ void k_residual_dd(int64_t n, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                              const double *__restrict__ values, const double *__restrict__ x,
+                              const double *__restrict__ b, double *__restrict__ r) {
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st) {
+        double hi = b[i], lo = 0.0;
+        for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) {
+            const double a = values[k], xv = x[indices[k]];
+            // round-to-nearest intrinsics: the compiler must not contract these into FMAs or reassociate them
+            const double p = -__dmul_rn(a, xv);
+            const double pe = -__fma_rn(a, xv, p);         // a * xv = -(p + pe) exactly
+            const double s = __dadd_rn(hi, p);             // two-sum of hi and p: hi + p = s + e exactly
+            const double bb = __dadd_rn(s, -hi);
+            const double e = __dadd_rn(__dadd_rn(hi, -__dadd_rn(s, -bb)), __dadd_rn(p, -bb));
+            hi = s;
+            lo = __dadd_rn(lo, __dadd_rn(e, pe));
+        }
+        r[i] = __dadd_rn(hi, lo);
+    }
+}
+
 inline unsigned vec_grid(int64_t n) {
     int64_t g = (n + VEC_THREADS - 1) / VEC_THREADS;
     const int64_t cap = (int64_t)sm_count() * 8;          // 8 x 256 threads = full residency
@@ -950,4 +975,12 @@ extern "C" int mwx_dcg_spmv_dot_lx(int64_t n, int64_t plan, const int64_t *indpt
     CgScalars *sc = ws_scalars(ws);
     return launch_spmv(n, plan, indptr, indices, values, x_ext, q, x_ext, &sc->pq, ws_partials(ws), &sc->ticket[0],
                        as_stream(stream), (const SpmvLX *)lx);
+}
+
+extern "C" int mwx_residual_dd(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values,
+                               const double *x, const double *b, double *r, void *stream) {
+    if (n <= 0 || !indptr || !indices || !values || !x || !b || !r) return MWX_E_BADARG;
+    k_residual_dd<<<vec_grid(n), VEC_THREADS, 0, as_stream(stream)>>>(n, indptr, indices, values, x, b, r);
+    MWX_LAUNCH_CHECK();
+    return 0;
 }

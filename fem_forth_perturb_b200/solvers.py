@@ -477,6 +477,44 @@ def pcg(A, b, tol=1e-5, maxiter=None, precondition=True, amg=None, reordering=No
 _run_pcg = pcg
 
 
+def residual_dd(A, x, b):
+    """r = b - A x on the device with double-double row accumulation, rounded once (``mwx_residual_dd``)."""
+    torch = L.require_cuda()
+    A = _to_device_csr(A)
+    ip = A.d_indptr if A.d_indptr.dtype == torch.int64 else A.d_indptr.to(torch.int64)
+    r = torch.empty_like(x)
+    L.check(L.lib().mwx_residual_dd(A.shape[0], L.ptr(ip), L.ptr(A.d_indices), L.ptr(A.d_data), L.ptr(x), L.ptr(b), L.ptr(r),
+                                    L.stream()), 'mwx_residual_dd')
+    return r
+
+
+def refine(A, b, x, steps=2, tol=1e-8, maxiter=None, amg=None, log=None):
+    """Mixed-precision iterative refinement of a PCG solution (an extension; the reference has none):
+    repeat ``steps`` times  r = b - A x in double-double,  d = PCG(A, r / ||r||) * ||r||,  x += d.
+    With the residual at twice the working precision the forward error goes to fp64 round-off level instead of
+    stalling at cond(A) * eps (1e-6 at 67 M DOFs), as long as cond(A) * eps < 1.  x, b: device tensors.
+    ``log`` = a list receiving one dict per step (exact relative residual before the step, inner iterations)."""
+    torch = L.require_cuda()
+    A = _to_device_csr(A)
+    bn = float(torch.linalg.norm(b))
+    x = x.clone()
+    for _ in range(int(steps)):
+        r = residual_dd(A, x, b)
+        rn = float(torch.linalg.norm(r))
+        entry = {'rel_residual_dd': rn / bn if bn > 0 else rn}
+        if log is not None:
+            log.append(entry)
+        if not rn > 0.0:
+            break
+        d, its, info, _ = pcg(A, r / rn, tol, maxiter, amg=amg, max_rechecks=2)    # unit right-hand side: scipy's absolute
+        x += rn * d                                                                 # early exit (||b|| <= tol) must not fire
+        entry.update(inner_iters=its, inner_info=info)
+    if log is not None:
+        rn = float(torch.linalg.norm(residual_dd(A, x, b)))
+        log.append({'rel_residual_dd': rn / bn if bn > 0 else rn})
+    return x
+
+
 def _reject_host_callables(kwargs):
     if kwargs.get('M') is not None:
         raise NotImplementedError("a user-supplied preconditioner M is a host callable; the device path "

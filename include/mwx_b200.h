@@ -418,6 +418,12 @@ int mwx_smoother_step_pk(int64_t n, int64_t nnz_hint, const int64_t *indptr, con
                          double *x_out, const double *b, const double *dinv, double *d, double c1, double c2,
                          void *stream);
 
+/* r = b - A x, every row accumulated in double-double and rounded once (no reference counterpart: the reference never ran
+ * meshes where it matters).  Used by the optional iterative refinement of `pcg(..., refine=k)`: with condition numbers
+ * ~1e10 the fp64 residual's own rounding error exceeds tol * ||b||, and the forward error stalls at ~1e-6. */
+int mwx_residual_dd(int64_t n, const int64_t *indptr, const int32_t *indices, const double *values, const double *x,
+                    const double *b, double *r, void *stream);
+
 /* Tile-local column plan of a CSR pattern (csrc/spmv_lx.cu; no reference counterpart).  The SpMV kernel is bound by the
  * L1 wavefronts of its x gathers (11.5 scattered columns per Morley row), not by DRAM; the rows of one tile share their
  * columns, so the plan lists each tile's DISTINCT columns once (sorted) and gives every nonzero a 2-byte index into that

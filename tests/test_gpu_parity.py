@@ -754,6 +754,44 @@ def test_tile_local_column_spmv(cuda):
     assert info0 == 0 and info1 == 0 and it0 == it1 and torch.equal(x0, x1)
 
 
+def test_double_double_residual_and_refinement(cuda):
+    """``mwx_residual_dd``: b - A x with double-double row accumulation - checked against exact rational arithmetic on a few
+    rows and against the fp64 residual's error; ``refine``: on an ill-conditioned system the forward error of a tol-1e-8
+    PCG solution drops by orders of magnitude (the plain solve stalls at cond * tol)."""
+    from fractions import Fraction
+    import fem_forth_perturb_b200 as F
+    torch = cuda
+    gm = F.MeshTri().refine(6)
+    basis = F.InteriorBasis(gm, F.ElementTriMorley())
+    K = F.asm_gpu(1.0 * F.a_load + F.b_load, basis)               # eps = 1: the fourth-order term dominates, cond ~ h^-4
+    bf = gm.boundary_facets()
+    D = np.concatenate((np.unique(gm.facets[:, bf]), bf + gm.nv))
+    Kc = F.condense(K, D=D, expand=False)
+    A = Kc.tocsr()
+    n = A.shape[0]
+    rng = np.random.default_rng(41)
+    xs = rng.standard_normal(n)
+    b = A @ xs
+    x_t, b_t = torch.from_numpy(xs).cuda(), torch.from_numpy(b).cuda()
+    r_dd = F.residual_dd(Kc, x_t, b_t).cpu().numpy()
+    rows = rng.choice(n, 40, replace=False)
+    exact = np.array([float(Fraction(b[i]) - sum(Fraction(A.data[k]) * Fraction(xs[A.indices[k]])
+                                                   for k in range(A.indptr[i], A.indptr[i + 1]))) for i in rows])
+    scale = np.abs(A[rows]).dot(np.abs(xs)) + np.abs(b[rows])
+    assert np.abs(r_dd[rows] - exact).max() <= 1e-30 * scale.max() + 2.3e-16 * np.abs(exact).max()      # one final rounding
+    r64 = b - A @ xs
+    assert np.abs(r64[rows] - exact).max() > 10 * np.abs(r_dd[rows] - exact).max()                       # fp64 is visibly worse
+    # refinement: b is exactly representable data; the system's true solution is x* up to cond * eps
+    ml = F.AMGHierarchy(Kc, mode='sa')
+    x0, it0, info0, _ = F.pcg(Kc, b_t, tol=1e-8, amg=ml)
+    log = []
+    x1 = F.refine(Kc, b_t, x0, steps=2, tol=1e-8, amg=ml, log=log)
+    e0 = float(torch.linalg.norm(x0 - x_t) / torch.linalg.norm(x_t))
+    e1 = float(torch.linalg.norm(x1 - x_t) / torch.linalg.norm(x_t))
+    assert info0 == 0 and len(log) == 3 and log[-1]['rel_residual_dd'] < 1e-3 * log[0]['rel_residual_dd'], log
+    assert e1 < 1e-2 * e0, (e0, e1)
+
+
 def test_locality_reordering_is_a_similarity_transform(cuda):
     """Fast-mode solvers run on P A P^T (Hilbert order of the DOF locations) and permute back."""
     import fem_forth_perturb_b200 as F
