@@ -289,7 +289,8 @@ class AMGHierarchy:
         """Inverse of the coarsest operator of a smoothed-aggregation hierarchy (symmetric positive definite: Galerkin
         products of an SPD matrix with full-rank prolongators, unit diagonal for dead coarse DOFs).  Up to 300 rows: the
         SVD of ``_pinv2``; larger: Cholesky on the device (setup only), symmetric eigendecomposition with ``_pinv2``'s
-        relative cutoff if the factorisation breaks down."""
+        relative cutoff if the factorisation breaks down.  (Host LAPACK dpotrf + dpotri was measured instead: 0.6 s at
+        3400 rows on 16 cores against 0.1 s here - but the first cuSOLVER call of a process costs 1-2 s of library load.)"""
         n = Ac.shape[0]
         if n <= 300:
             return cls._pinv2(Ac)

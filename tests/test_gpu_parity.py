@@ -792,6 +792,21 @@ def test_double_double_residual_and_refinement(cuda):
     assert e1 < 1e-2 * e0, (e0, e1)
 
 
+def test_coarse_inverse_of_the_sa_hierarchy(cuda):
+    """AMGHierarchy._pinv_coarse above 300 rows (device, setup only): Cholesky inverse of an SPD coarse operator,
+    pseudo-inverse with pinv2's cutoff when the factorisation breaks down."""
+    import fem_forth_perturb_b200 as F
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((700, 700))
+    A = B @ B.T + 700 * np.eye(700)
+    P = F.AMGHierarchy._pinv_coarse(A)
+    assert abs(P @ A - np.eye(700)).max() <= 1e-11 and abs(P - P.T).max() <= 1e-13 * abs(P).max()
+    B = rng.standard_normal((400, 395))
+    A = B @ B.T
+    P = F.AMGHierarchy._pinv_coarse(A)
+    assert abs(A @ P @ A - A).max() <= 1e-9 * abs(A).max()
+
+
 def test_locality_reordering_is_a_similarity_transform(cuda):
     """Fast-mode solvers run on P A P^T (Hilbert order of the DOF locations) and permute back."""
     import fem_forth_perturb_b200 as F

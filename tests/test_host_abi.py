@@ -55,6 +55,19 @@ def test_bench_launch_count_matches_the_profiled_cycle():
     assert 'launches 138' in listing
 
 
+def test_coarse_inverse_small_is_pinv2():
+    """AMGHierarchy._pinv_coarse up to 300 rows = scipy 1.4.1 pinv2 semantics (SVD with the 1e6 * eps cutoff)."""
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((40, 40))
+    A = B @ B.T + 40 * np.eye(40)
+    P = F.AMGHierarchy._pinv_coarse(A)
+    assert abs(P @ A - np.eye(40)).max() <= 1e-11
+    B = rng.standard_normal((60, 55))
+    A = B @ B.T                                                     # rank deficient: singular values below the cutoff are dropped
+    P = F.AMGHierarchy._pinv_coarse(A)
+    assert abs(A @ P @ A - A).max() <= 1e-10 * abs(A).max()
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
