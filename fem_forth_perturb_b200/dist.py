@@ -4,9 +4,13 @@
   follow a Hilbert curve.  The solver numbering is (part, curve position), so every rank owns a contiguous
   row block [lo, hi) and the user-visible skfem numbering is only touched at the boundary.
 * assembly: every rank assembles the matrix rows it owns (``mwx_assemble_morley_rows``) - no communication.
-* PCG: per iteration one halo exchange of p (neighbour point-to-point) and three small all-reduces
-  (p.Ap; r.r [+ r.z]); the preconditioner is Jacobi, or block-Jacobi AMG: each rank runs the single-GPU V-cycle
-  on its own diagonal block (iteration counts then depend on P - bench.py reports them).
+* PCG: per iteration one halo exchange of p and three small all-reduces (p.Ap; r.r [+ r.z]); the preconditioner is
+  Jacobi, the GLOBAL AMG hierarchy applied as a collective V-cycle (:class:`DistAMG`: row-blocked upper levels,
+  replicated tail), or block-Jacobi AMG (each rank's own diagonal block; iteration counts then depend on P).
+* communication: :class:`PeerComm` (default in bench.py) makes every exchange of an iteration - halo push fused with
+  an epoch-flag barrier, all-reduce, all-gather - a kernel storing into peer memory over NVLink, so iterations 2.. are
+  ONE CUDA-graph launch each; :class:`SymmMemComm` (push kernel + symmetric-memory barrier + NCCL all-reduce) and
+  :class:`TorchDistComm` (NCCL / gloo send-recv) are the fallbacks.
 
 The driver code is written once over a list of ``parts``: with ``torch.distributed`` the list holds this
 rank's part (one process per GPU, NCCL); with :class:`InProcessComm` it holds all P parts of one process,
