@@ -35,8 +35,17 @@ __device__ __forceinline__ void bsr_finish(int64_t r, double sum, const double *
     y[r] = sum;
 }
 
+// CTAs per SM the kernels are compiled for (register cap): 4 x 256 threads at 64 registers.  Measured on the level-12
+// SA iteration (ms per iteration): unconstrained (rows3 64 / rows1 72 registers, 3 CTAs for rows1) 22.96; 4 / 4: 21.64;
+// 5 / 4 (rows3 at 48 registers) 23.41; 6 / 5 spills.
+#ifndef MWX_BSR3_MINB
+#define MWX_BSR3_MINB 4
+#endif
+#ifndef MWX_BSR1_MINB
+#define MWX_BSR1_MINB 4
+#endif
 template <typename VT, int BC, int MODE>
-__global__ void __launch_bounds__(256) k_bsr_rows3(int64_t nbrows, int64_t nblocks, const int64_t *__restrict__ bptr,
+__global__ void __launch_bounds__(256, MWX_BSR3_MINB) k_bsr_rows3(int64_t nbrows, int64_t nblocks, const int64_t *__restrict__ bptr,
                                                    const int32_t *__restrict__ bidx, const VT *__restrict__ bval,
                                                    const double *__restrict__ x, double *y, const double *cvec,
                                                    BsrSmoother sm, int lpr) {
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(256) k_bsr_rows3(int64_t nbrows, int64_t nbloc
 }
 
 template <typename VT, int MODE>
-__global__ void __launch_bounds__(256) k_bsr_rows1(int64_t nrows, int64_t nblocks, const int64_t *__restrict__ bptr,
+__global__ void __launch_bounds__(256, MWX_BSR1_MINB) k_bsr_rows1(int64_t nrows, int64_t nblocks, const int64_t *__restrict__ bptr,
                                                    const int32_t *__restrict__ bidx, const VT *__restrict__ bval,
                                                    const double *__restrict__ x, double *y, const double *cvec,
                                                    BsrSmoother sm) {
